@@ -1,0 +1,257 @@
+"""Generate tests/golden/*.npz by running the UNMODIFIED reference.
+
+Run in the dev container only (needs /root/reference, which does not exist on the GPU
+box):   python oracle/make_golden.py
+The reference modules are imported through `oracle/refshim` (a CSR-backed `dgl` stand-in
+plus empty matplotlib/implicit/fastnode2vec stubs).  Every array written here is an
+OUTPUT OF THE REFERENCE on synthetic inputs that are stored alongside it, so the GPU-box
+tests never need the reference.  Test infrastructure; not imported by the product.
+"""
+import os
+import sys
+import tempfile
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+sys.path.insert(0, os.path.join(HERE, "refshim"))
+sys.path.insert(1, "/root/reference")
+sys.path.insert(2, ROOT)
+
+import dgl  # noqa: E402  (the shim)
+import pinsage_model as ref_psm  # noqa: E402  (the reference)
+import pinsage_training as ref_pst  # noqa: E402
+from oracle import oracle  # noqa: E402
+
+OUT = os.path.join(ROOT, "tests", "golden")
+os.makedirs(OUT, exist_ok=True)
+
+
+def synth_bipartite(n_tracks, n_cols, deg, rng):
+    """Small random bipartite track-collection graph, both edge directions listed (as in
+    graph.json, dataset_creation/get_data.py:211-214).  Every node gets degree >= 1."""
+    pairs = set()
+    for t in range(n_tracks):
+        for c in rng.choice(n_cols, size=min(n_cols, max(1, rng.poisson(deg))), replace=False):
+            pairs.add((t, int(c)))
+    for c in range(n_cols):
+        pairs.add((int(rng.randint(n_tracks)), c))
+    pairs = sorted(pairs)
+    t = np.array([p[0] for p in pairs]); c = np.array([p[1] for p in pairs]) + n_tracks
+    src = np.concatenate([t, c]); dst = np.concatenate([c, t])
+    perm = rng.permutation(src.shape[0])  # file order is arbitrary
+    return src[perm], dst[perm]
+
+
+def make_graph(n_tracks, n_cols, deg, seed):
+    rng = np.random.RandomState(seed)
+    src, dst = synth_bipartite(n_tracks, n_cols, deg, rng)
+    g = dgl.DGLGraph()
+    g.add_nodes(n_tracks + n_cols)
+    g.add_edges(src, dst)
+    indptr, indices = g.csr()
+    return g, indptr, indices.astype(np.int32)
+
+
+def gen_walk_topt():
+    out = {}
+    for tag, (nt, nc, deg, nsrc, seed) in {"a": (120, 30, 3, 48, 11), "b": (2000, 300, 12, 12, 12)}.items():
+        g, indptr, indices = make_graph(nt, nc, deg, seed)
+        rng = np.random.RandomState(seed + 100)
+        nodeset = torch.from_numpy(rng.choice(nt, size=nsrc, replace=False).astype(np.int64))
+        torch.manual_seed(seed)
+        trace = ref_psm.do_random_walks(g, nodeset, 500, 0.85)
+        out[f"{tag}_indptr"], out[f"{tag}_indices"] = indptr, indices
+        out[f"{tag}_n_tracks"] = np.int64(nt)
+        out[f"{tag}_nodeset"] = nodeset.numpy()
+        out[f"{tag}_trace"] = trace.numpy().astype(np.int32)
+        for T in (3, 100):
+            torch.manual_seed(seed)  # same mt19937 stream -> the same trace inside
+            w, nb = ref_psm.sample_neighborhood_topt(g, nt, nodeset, 500, 0.85, T)
+            out[f"{tag}_w_T{T}"], out[f"{tag}_nb_T{T}"] = w.numpy(), nb.numpy()
+    np.savez_compressed(os.path.join(OUT, "walk_topt.npz"), **out)
+    print("walk_topt", {k: v.shape for k, v in out.items()})
+
+
+def gen_walk_dist():
+    """Long reference walks for the statistical check of the Philox walker."""
+    g, indptr, indices = make_graph(120, 30, 3, 11)
+    nodeset = torch.tensor([0, 7, 19, 42, 77, 101])
+    torch.manual_seed(5)
+    n_hops = 20000
+    trace = ref_psm.do_random_walks(g, nodeset, n_hops, 0.85)
+    counts = np.stack([np.bincount(trace[i].numpy(), minlength=150) for i in range(len(nodeset))])
+    np.savez_compressed(os.path.join(OUT, "walk_dist.npz"), indptr=indptr, indices=indices, n_tracks=np.int64(120),
+                        nodeset=nodeset.numpy(), n_hops=np.int64(n_hops), counts=counts.astype(np.int32))
+    print("walk_dist", counts.shape)
+
+
+def random_nbhds(n, Tp, rng, zero_tail_rows=0):
+    """Neighbourhood tables shaped like precompute_neighborhoods_topt's output
+    (pinsage_model.py:119-132): weights = visit counts / 500, descending."""
+    nodes = np.stack([rng.choice(n, size=Tp, replace=False) for _ in range(n)]).astype(np.int64)
+    counts = np.sort(rng.randint(1, 40, size=(n, Tp)), axis=1)[:, ::-1]
+    w = counts.astype(np.float64) / 500.0
+    return np.ascontiguousarray(w), nodes
+
+
+def gen_frontier():
+    rng = np.random.RandomState(3)
+    n = 400
+    w, nodes = random_nbhds(n, 20, rng)
+    out = {"w": w, "nodes": nodes}
+    for tag, (L, T, B) in {"L2T3": (2, 3, 64), "L3T5": (3, 5, 16), "L2T10": (2, 10, 32)}.items():
+        nodeset = rng.randint(0, n, size=B).astype(np.int64)  # duplicates on purpose
+        S = ref_psm.relevant_nodes_per_layer_precomp(torch.from_numpy(nodeset), L, T,
+                                                     (torch.from_numpy(w), torch.from_numpy(nodes)))
+        out[f"{tag}_nodeset"] = nodeset
+        for l, (ns, ww, nb) in enumerate(S):
+            out[f"{tag}_ns{l}"], out[f"{tag}_w{l}"], out[f"{tag}_nb{l}"] = ns.numpy(), ww.numpy(), nb.numpy()
+    np.savez_compressed(os.path.join(OUT, "frontier.npz"), **out)
+    print("frontier ok")
+
+
+def build_ref_model(n, L, dims, T, nbhds, params):
+    model = ref_psm.PinSageModel(None, n, L, dims, 500, 0.85, T, nbhds)
+    model.load_state_dict(params)
+    return model
+
+
+def subsample(t, stride=97):
+    return t.reshape(-1)[::stride].clone()
+
+
+def gen_model(tag, n, dims, L, T, B, seed, full_grads):
+    rng = np.random.RandomState(seed)
+    features = torch.tensor(rng.standard_normal((n, dims[0])), dtype=torch.float32)
+    w, nodes = random_nbhds(n, max(T, 12), rng)
+    nbhds = (torch.from_numpy(w), torch.from_numpy(nodes))
+    params = oracle.make_params(L, dims, np.random.RandomState(seed + 1))
+    model = build_ref_model(n, L, dims, T, nbhds, params)
+    batch = rng.randint(0, n, size=(B, 3)).astype(np.int64)
+    batch[1, 0] = batch[0, 0]; batch[2, 0] = batch[0, 0]; batch[5, 1] = batch[4, 1]  # duplicates per column
+    bt = torch.from_numpy(batch)
+    out = {"seed": np.int64(seed), "n": np.int64(n), "dims": np.array(dims), "L": np.int64(L), "T": np.int64(T),
+           "w": w, "nodes": nodes, "batch": batch}
+    # single conv layer on its own (layer 0 over the layer-0 frontier of column 0)
+    S = ref_psm.relevant_nodes_per_layer_precomp(bt[:, 0], L, T, nbhds)
+    ns0, w0, nb0 = S[0]
+    out["conv0_out"] = model.conv_layers[0](features, ns0, nb0, w0).detach().numpy()
+    # forward of one call + linear-functional gradient (exposes the duplicate factor)
+    R = torch.tensor(rng.standard_normal((B, dims[2])), dtype=torch.float32)
+    model.zero_grad()
+    emb = model(features, bt[:, 0])
+    (emb * R).sum().backward()
+    out["R"] = R.numpy(); out["emb_q"] = emb.detach().numpy()
+    for k, p in model.named_parameters():
+        out[f"lin_grad/{k}"] = p.grad.numpy().copy() if full_grads else subsample(p.grad).numpy()
+        out[f"lin_gradnorm/{k}"] = p.grad.norm().numpy()
+    # the training triple: three forwards + max-margin loss + backward (pinsage_training.py:184-190)
+    for margin_tag, margin in (("m1e-5", 1e-5), ("m0.5", 0.5)):
+        model.zero_grad()
+        hq, hp, hn = model(features, bt[:, 0]), model(features, bt[:, 1]), model(features, bt[:, 2])
+        loss = ref_pst.max_margin_loss(hq, hp, hn, margin)
+        loss.backward()
+        out[f"{margin_tag}/loss"] = loss.detach().numpy()
+        out[f"{margin_tag}/hq"], out[f"{margin_tag}/hp"], out[f"{margin_tag}/hn"] = (x.detach().numpy() for x in (hq, hp, hn))
+        for k, p in model.named_parameters():
+            out[f"{margin_tag}/grad/{k}"] = p.grad.numpy().copy() if full_grads else subsample(p.grad).numpy()
+            out[f"{margin_tag}/gradnorm/{k}"] = p.grad.norm().numpy()
+    np.savez_compressed(os.path.join(OUT, f"model_{tag}.npz"), **out)
+    print("model", tag, "loss", out["m1e-5/loss"], out["m0.5/loss"])
+
+
+def gen_train_steps():
+    """Three optimiser steps of the reference trainer (`PinSage.train_batch`,
+    pinsage_training.py:181-214) from a fixed state and fixed batches."""
+    rng = np.random.RandomState(21)
+    n, din = 220, 160  # Din >= out_dim (128) or put_embeddings pads negatively (pinsage_model.py:27)
+    features = torch.tensor(rng.standard_normal((n, din)), dtype=torch.float32)
+    w, nodes = random_nbhds(n, 100, rng)
+    positives = torch.from_numpy(rng.randint(0, n, size=(500, 2)).astype(np.int64))
+    batches = rng.randint(0, n, size=(3, 32, 3)).astype(np.int64)
+    params = oracle.make_params(2, (din, 512, 128), np.random.RandomState(22))
+    cwd = os.getcwd()
+    with tempfile.TemporaryDirectory() as tmp:
+        os.chdir(tmp)
+        os.mkdir("runs")
+        g = dgl.DGLGraph()
+        g.nbhds_path = os.path.join(tmp, "neighborhoods.pt")
+        torch.save((torch.from_numpy(w), torch.from_numpy(nodes)), g.nbhds_path)
+        trainer = ref_pst.PinSage(g, n, features, positives, log=False, load_save=False)
+        os.chdir(cwd)
+    trainer.model.load_state_dict(params)
+    losses = []
+    for b in batches:
+        loss, _, _ = trainer.train_batch(torch.from_numpy(b))
+        losses.append(float(loss))
+    out = {"n": np.int64(n), "din": np.int64(din), "w": w, "nodes": nodes, "batches": batches,
+           "losses": np.array(losses, dtype=np.float64)}
+    for k, p in trainer.model.named_parameters():
+        out[f"param_sub/{k}"] = subsample(p.detach(), 53).numpy()
+        out[f"param_delta_norm/{k}"] = (p.detach() - params[k]).norm().numpy()
+    emb = trainer.embed(torch.arange(0, 40))
+    out["emb_after"] = emb.detach().numpy()
+    np.savez_compressed(os.path.join(OUT, "train_steps.npz"), **out)
+    print("train_steps losses", losses)
+
+
+def gen_loss():
+    rng = np.random.RandomState(8)
+    out = {}
+    for tag, (B, d, margin, scale) in {"a": (2, 8, 1e-5, 1.0), "b": (37, 128, 1e-5, 1.0), "c": (128, 128, 0.3, 3.0), "d": (64, 32, 0.0, 1e-3)}.items():
+        xs = [torch.tensor(rng.standard_normal((B, d)) * scale, dtype=torch.float32, requires_grad=True) for _ in range(3)]
+        loss = ref_pst.max_margin_loss(xs[0], xs[1], xs[2], margin)
+        loss.backward()
+        out[f"{tag}_margin"] = np.float64(margin)
+        for nm, x in zip("qpn", xs):
+            out[f"{tag}_{nm}"] = x.detach().numpy(); out[f"{tag}_d{nm}"] = x.grad.numpy()
+        out[f"{tag}_loss"] = loss.detach().numpy()
+    np.savez_compressed(os.path.join(OUT, "loss.npz"), **out)
+    print("loss ok")
+
+
+def gen_metrics_knn():
+    for stub in ("implicit", "fastnode2vec"):
+        d = os.path.join(HERE, "refshim", stub)
+        assert os.path.isdir(d), f"missing stub {d}"
+    import eval as ref_eval  # noqa  (reference eval.py)
+    import baselines as ref_bl  # noqa
+    out = {}
+    # the commented-out toy vectors of eval.py:660-683 (entered by hand, not copied code)
+    toy_pos = torch.tensor([[0, 1], [0, 5], [3, 4], [4, 2], [5, 6], [6, 7]])
+    toy_knn = torch.tensor([[0, 1, 5, 6, 7], [1, 0, 6, 5, 7], [2, 4, 3, 0, 1], [3, 4, 2, 7, 6],
+                            [4, 2, 3, 0, 1], [5, 6, 0, 1, 7], [6, 5, 7, 3, 1], [7, 6, 5, 0, 1]])
+    out["toy_pos"], out["toy_knn"] = toy_pos.numpy(), toy_knn.numpy()
+    out["toy_K"] = np.array([1, 2, 3, 5])
+    out["toy_hr"] = np.array([ref_eval.hit_rate(toy_knn, toy_pos, K) for K in (1, 2, 3, 5)])
+    out["toy_mrr"] = np.array([ref_eval.mrr(toy_knn, toy_pos, K) for K in (1, 2, 3, 5)])
+    rng = np.random.RandomState(4)
+    knn = np.stack([rng.permutation(200)[:50] for _ in range(200)]).astype(np.int64)
+    pos = rng.randint(0, 200, size=(300, 2)).astype(np.int64)
+    out["rnd_knn"], out["rnd_pos"] = knn, pos
+    out["rnd_K"] = np.array([1, 10, 25, 50])
+    out["rnd_hr"] = np.array([ref_eval.hit_rate(torch.from_numpy(knn), torch.from_numpy(pos), K) for K in (1, 10, 25, 50)])
+    out["rnd_mrr"] = np.array([ref_eval.mrr(torch.from_numpy(knn), torch.from_numpy(pos), K) for K in (1, 10, 25, 50)])
+    emb = torch.tensor(rng.standard_normal((300, 32)), dtype=torch.float32)
+    q = torch.arange(0, 300)
+    kw, kn = ref_bl.knn_from_emb(emb, q, 10, None)
+    out["knn_emb"], out["knn_w"], out["knn_n"] = emb.numpy(), kw.numpy(), kn.numpy()
+    np.savez_compressed(os.path.join(OUT, "metrics_knn.npz"), **out)
+    print("metrics", out["toy_hr"], out["toy_mrr"])
+
+
+if __name__ == "__main__":
+    which = sys.argv[1:] or ["walk_topt", "walk_dist", "frontier", "model", "train_steps", "loss", "metrics_knn"]
+    if "walk_topt" in which: gen_walk_topt()
+    if "walk_dist" in which: gen_walk_dist()
+    if "frontier" in which: gen_frontier()
+    if "model" in which:
+        gen_model("small", 150, (64, 96, 32), 2, 5, 40, 31, full_grads=True)
+        gen_model("l3", 180, (96, 64, 32), 3, 4, 24, 41, full_grads=True)
+        gen_model("default", 300, (512, 512, 128), 2, 3, 128, 51, full_grads=False)
+    if "train_steps" in which: gen_train_steps()
+    if "loss" in which: gen_loss()
+    if "metrics_knn" in which: gen_metrics_knn()

@@ -1,0 +1,1 @@
+"""Empty import-time stub (oracle/make_golden.py only)."""
