@@ -1,0 +1,40 @@
+// C-ABI plumbing: version, error text, device selection and the ps_gemm dispatcher.
+#include "common.cuh"
+#include "../../include/pinsage_b200.h"
+#include <cstdarg>
+
+char* ps_err_buf() {
+    static thread_local char buf[512] = {0};
+    return buf;
+}
+
+int ps_fail(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(ps_err_buf(), 512, fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+int ps_gemm_simt_launch(const float* P, int64_t ldp, int p_kmajor, const int32_t* p_rows,
+                        const float* Q, int64_t ldq, int q_kmajor, const int32_t* q_rows,
+                        float* C, int64_t ldc, int64_t M, int64_t N, int64_t K,
+                        const float* bias, int act, int l2norm, float* norm_out, int accumulate, int splits,
+                        cudaStream_t stream);
+
+extern "C" int ps_version(void) { return PS_ABI_VERSION; }
+extern "C" const char* ps_last_error(void) { return ps_err_buf(); }
+
+extern "C" int ps_set_device(int device) {
+    PS_CUDA_CHECK(cudaSetDevice(device));
+    return PS_OK;
+}
+
+extern "C" int ps_gemm(const float* P, int64_t ldp, int p_kmajor, const int32_t* p_rows,
+                       const float* Q, int64_t ldq, int q_kmajor, const int32_t* q_rows,
+                       float* C, int64_t ldc, int64_t M, int64_t N, int64_t K,
+                       const float* bias, int act, int l2norm, float* norm_out, int accumulate, int splits,
+                       ps_stream_t stream) {
+    return ps_gemm_simt_launch(P, ldp, p_kmajor, p_rows, Q, ldq, q_kmajor, q_rows, C, ldc, M, N, K, bias, act, l2norm,
+                               norm_out, accumulate, splits, static_cast<cudaStream_t>(stream));
+}

@@ -1,0 +1,329 @@
+"""B200 drop-in for the reference's `pinsage_training` module: same public names,
+attributes and file formats (reference: /root/reference/pinsage_training.py).
+
+`PinSage.train_batch` runs the fused device step of ps_engine.Engine.train_step (one
+shared frontier for the q / pos / neg columns, max-margin loss + backward in CUDA,
+then the optimiser).  Batch construction runs on the device without the O(P) randperm
+and O(N) mask of the reference (pinsage_training.py:53-77) but draws from the same law.
+wandb logging is optional (only imported when log=True).
+"""
+from __future__ import annotations
+
+import os
+import time
+
+import torch
+import torch.nn.functional as F
+from tqdm import tqdm
+
+import pinsage_model as psm
+import ps_native
+
+BASE_RUN_DIR = "./runs"
+
+
+def max_margin_loss(h_q, h_pos, h_neg, margin):
+    """mean(max(q^.n^ - q^.p^ + margin, 0)) with F.normalize'd rows
+    (pinsage_training.py:31-41).  CUDA inputs run the fused loss kernel (forward only here;
+    autograd users get the torch expression so gradients flow)."""
+    if h_q.requires_grad or h_pos.requires_grad or h_neg.requires_grad or not h_q.is_cuda:
+        h_q, h_pos, h_neg = F.normalize(h_q, dim=1), F.normalize(h_pos, dim=1), F.normalize(h_neg, dim=1)
+        d = (h_q * h_neg).sum(1) - (h_q * h_pos).sum(1) + margin
+        return torch.stack([d, torch.zeros_like(d)], 1).max(1).values.mean()
+    B = h_q.shape[0]
+    emb = torch.cat([h_q, h_pos, h_neg], 0).to(torch.float32).contiguous()
+    idx = torch.arange(B, device="cuda", dtype=torch.int32)
+    triples = torch.stack([idx, idx + B, idx + 2 * B], 1).contiguous()
+    loss = torch.zeros(1, dtype=torch.float32, device="cuda")
+    ps_native.margin_loss_fwd_bwd(emb, triples, margin, 1.0, None, loss, None)
+    return loss[0]
+
+
+def cosine_dissimilarity(a, b):
+    return 1 - F.cosine_similarity(a, b)
+
+
+COSINE_TRIPLET_LOSS = torch.nn.TripletMarginWithDistanceLoss(distance_function=cosine_dissimilarity,
+                                                            margin=0.0001, reduction="mean")
+
+
+# ---- batch construction ----------------------------------------------------------------
+
+def _distinct_randint(high, k, device):
+    """k distinct uniform draws from [0, high) without an O(high) permutation: same law as
+    randperm(high)[:k] (pinsage_training.py:58,74).  Falls back to randperm when k is a
+    large fraction of high."""
+    if k > high:
+        k = high
+    if high <= 4 * k or high < 65536:
+        return torch.randperm(high, device=device)[:k]
+    out = torch.empty(0, dtype=torch.int64, device=device)
+    while out.numel() < k:
+        cand = torch.randint(0, high, (int(1.25 * k) + 16,), device=device)
+        cand = torch.cat([out, cand])
+        # keep first occurrences in draw order (a uniformly random k-subset in random order)
+        uniq, inv = torch.unique(cand, return_inverse=True)
+        first = torch.full((uniq.numel(),), cand.numel(), dtype=torch.int64, device=device)
+        first.scatter_reduce_(0, inv, torch.arange(cand.numel(), device=device), reduce="amin")
+        out = cand[torch.sort(first).values]
+    return out[:k]
+
+
+def sample_positives_with_rep(positives, batch_size):
+    """batch_size distinct random rows of `positives` (pinsage_training.py:53-62)."""
+    sample = _distinct_randint(positives.shape[0], batch_size, positives.device)
+    return positives[sample, :].to(torch.int64)
+
+
+def sample_easy_negatives(all_ids, pos_batch):
+    """One random node per pair, distinct, none of them in the positive batch
+    (pinsage_training.py:64-77)."""
+    n, B = all_ids.shape[0], pos_batch.shape[0]
+    pos_nodeset = pos_batch.flatten().unique()
+    if n - pos_nodeset.numel() < 8 * B or n < 65536:  # small id space: the reference's mask + randperm
+        mask = torch.ones((n,), dtype=torch.bool, device=all_ids.device)
+        mask[pos_nodeset] = False
+        possible = all_ids[mask].to(torch.int64)
+        negatives = possible[torch.randperm(possible.numel(), device=all_ids.device)[:B]]
+    else:  # rejection sampling: uniform without replacement from the same set
+        negatives = torch.empty(0, dtype=torch.int64, device=all_ids.device)
+        while negatives.numel() < B:
+            cand = _distinct_randint(n, 2 * B, all_ids.device)
+            cand = cand[~torch.isin(cand, pos_nodeset)]
+            negatives = torch.cat([negatives, cand[~torch.isin(cand, negatives)]])
+        negatives = all_ids[negatives[:B]].to(torch.int64)
+    batch = torch.cat((pos_batch, negatives.unsqueeze(1)), dim=1)
+    nodeset = batch.flatten().unique().to(torch.int64)
+    return batch, nodeset
+
+
+def sample_hard_negatives(all_ids, pos_batch, nbhds, min_rank, max_rank, reference_compat=True):
+    """One hard negative per pair: the query's PPR neighbour at a random rank in
+    [min_rank, max_rank) (pinsage_training.py:79-87).  The reference gathers rows 0..B-1 of
+    the neighbourhood table instead of the queries' rows (:84); reference_compat=True
+    reproduces that, False uses the queries' rows."""
+    queries = pos_batch[:, 0]
+    nb_nodes = nbhds[1]
+    rnd_ranks = torch.randint(min_rank, max_rank, (queries.shape[0],), device=pos_batch.device)
+    rows = torch.arange(queries.shape[0], device=pos_batch.device) if reference_compat else queries
+    hard_neg = nb_nodes.to(pos_batch.device)[rows, rnd_ranks].to(torch.int64)
+    batch = torch.cat((pos_batch, hard_neg.unsqueeze(1)), dim=1)
+    nodeset = batch.flatten().unique().to(torch.int64)
+    return batch, nodeset
+
+
+def sample_batch(all_ids, positives, batch_size, nbhds, hard_negatives=True, hn_min=10, hn_max=100):
+    """(batch int64 [B,3], nodeset) (pinsage_training.py:89-97)."""
+    pos_batch = sample_positives_with_rep(positives, batch_size)
+    if hard_negatives:
+        return sample_hard_negatives(all_ids, pos_batch, nbhds, hn_min, hn_max)
+    return sample_easy_negatives(all_ids, pos_batch)
+
+
+def batch_variance(h):
+    """pinsage_training.py:99-103."""
+    mean = torch.mean(h, dim=0)
+    var = torch.sum(torch.pow(h - mean, 2)) / (h.shape[0] - 1)
+    return torch.prod(var)
+
+
+# ---- trainer -----------------------------------------------------------------------------
+
+class PinSage():
+    """The PinSage trainer (pinsage_training.py:108-295): same constructor, hyper-parameter
+    attributes, methods and checkpoint format.  Features, graph, neighbourhood table and
+    positives are resident in HBM after construction; `train_batch` accepts host or device
+    batches."""
+
+    def __init__(self, g, n_items, features, positives, log=True, load_save=True):
+        self.run_name = "pinsage_randomft_intersect"
+        self.precomp_path = getattr(g, "nbhds_path", None)
+
+        self.g = g
+        self.n = n_items
+        self.all_ids = torch.arange(0, n_items, 1, dtype=torch.int64, device="cuda")
+        self.features = features
+        self.positives = positives
+
+        self.n_layers = 2
+        self.in_dim = features.shape[1]
+        self.hidden_dim = 512
+        self.out_dim = 128
+        self.dimensions = (self.in_dim, self.hidden_dim, self.out_dim)
+        self.n_hops = 500
+        self.alpha = 0.85
+        self.T = 3
+        self.hard_negatives = False
+        self.hn_min = 10
+        self.hn_max = 100
+
+        self.nbhds = psm.precompute_neighborhoods_topt(self.g, self.n, self.n_hops, self.alpha,
+                                                       psm.DEF_T_PRECOMP, self.precomp_path)
+        self.model = psm.PinSageModel(self.g, self.n, self.n_layers, self.dimensions,
+                                      self.n_hops, self.alpha, self.T, self.nbhds)
+
+        self.lr = 1e-4
+        self.decay = 0.95
+        self.optimizer = torch.optim.Adam(self.model.parameters(), lr=self.lr)
+        self.scheduler = torch.optim.lr_scheduler.ExponentialLR(self.optimizer, self.decay)
+        self.margin = 1e-5
+        self.epochs = 30
+        self.batch_size = 128
+        self.b_per_e = 500
+
+        self.embeddings = None
+        self.reference_compat = True   # duplicate-node gradient factor, hard-negative row quirk
+        self.diagnostics = True        # node-feature loss + batch variance, as train_batch returns them
+        self.world_size, self.rank = 1, 0  # set by ps_dist.attach() for data-parallel runs
+        self._grad_sync = None
+
+        run_dir = os.path.join(BASE_RUN_DIR, self.run_name)
+        os.makedirs(os.path.join(run_dir, "board"), exist_ok=True)
+
+        self.e = 0
+        self.b = 0
+
+        self.log = log
+        if self.log:
+            import wandb
+            self._wandb = wandb
+            wandb.config = {"learning_rate": self.lr, "epochs": self.epochs, "batch_size": self.batch_size}
+            wandb.init(project='gcn-song-embeddings', name=self.run_name)
+            wandb.watch(self.model, log="all", log_freq=10, log_graph=True)
+
+        self.load_save = load_save
+        if self.load_save:
+            self.load_model()
+
+    # device-resident views of the inputs
+    def _feats(self):
+        return self.model.engine.features(self.features)
+
+    def _positives_dev(self):
+        p = getattr(self, "_pos_dev", None)
+        if p is None or p.shape != self.positives.shape or getattr(self, "_pos_src", None) is not self.positives:
+            self._pos_dev = self.positives.to("cuda", torch.int64)
+            self._pos_src = self.positives
+        return self._pos_dev
+
+    def train_batch(self, batch):
+        """One optimiser step on a batch of (q, pos, neg) triples (pinsage_training.py:181-214).
+        Returns (loss, node_feat_loss, variance) as 0-dim device tensors."""
+        if not self.reference_compat:
+            self.model.T = self.T  # the reference never re-reads T after construction (grid_search.py:46-47)
+        batch = torch.as_tensor(batch).to("cuda", torch.int64, non_blocking=True)
+        feats = self._feats()
+        loss, emb, triples = self.model.engine.train_step(feats, batch, self.margin, self.reference_compat)
+        if self._grad_sync is not None:
+            self._grad_sync()
+        self.optimizer.step()
+        if self.diagnostics:
+            with torch.no_grad():
+                norm = F.normalize
+                node_feat_loss = COSINE_TRIPLET_LOSS(norm(feats[batch[:, 0], :], dim=1),
+                                                     norm(feats[batch[:, 1], :], dim=1),
+                                                     norm(feats[batch[:, 2], :], dim=1))
+                variance = batch_variance(emb[triples[:, 0].long()])
+        else:
+            node_feat_loss = variance = torch.zeros((), device="cuda")
+        return loss[0], node_feat_loss, variance
+
+    def train(self):
+        """Train the model (pinsage_training.py:216-256)."""
+        print("\033[0;33mTraining PinSage...\033[0m")
+        positives = self._positives_dev()
+        while self.e < self.epochs:
+            print(f"Training epoch {self.e+1}/{self.epochs}...")
+            cur_lr = self.optimizer.param_groups[0]["lr"]
+            t1 = time.time()
+            pbar = tqdm(total=self.b_per_e)
+            pbar.update(1)
+            while self.b < self.b_per_e:
+                batch, _ = sample_batch(self.all_ids, positives, self.batch_size, self.nbhds,
+                                        hard_negatives=self.hard_negatives, hn_min=self.hn_min, hn_max=self.hn_max)
+                loss, node_feat_loss, variance = self.train_batch(batch)
+                pbar.update(1)
+                if self.b % 50 == 0:  # reading the loss synchronises the device: not every step
+                    pbar.set_description(f"Loss = {float(loss)}, bathes done")
+                if self.log:
+                    self._wandb.log({'Train Loss': loss, 'Node Features Loss': node_feat_loss,
+                                     'Batch Variance': variance, 'Learning Rate': cur_lr})
+                if self.load_save:
+                    self.save_model()
+                self.b += 1
+            print(f"{time.time() - t1}s elapsed.")
+            pbar.close()
+            self.b = 0
+            self.e += 1
+            self.scheduler.step()
+
+    def embed(self, ids=None, bsize=None):
+        """Node embeddings, optionally only for `ids` / in `bsize` batches
+        (pinsage_training.py:258-275; like the reference, bsize ignores ids and embeds rows
+        0..n-1).  Returned on the host, as the reference's callers expect."""
+        if ids is None:
+            ids = self.all_ids
+        self.model.eval()
+        if not self.reference_compat:
+            self.model.T = self.T
+        feats = self._feats()
+        n = len(ids)
+        if not bsize:
+            out = self.model.engine.embed(feats, torch.as_tensor(ids).to("cuda", torch.int64))
+        else:
+            out = torch.zeros((n, self.out_dim), device="cuda")
+            for i in range(0, n, bsize):
+                rng = torch.arange(i, min(i + bsize, n), device="cuda")
+                out[rng, :] = self.model.engine.embed(feats, rng)
+        self.embeddings = out.cpu()
+        return self.embeddings
+
+    def load_model(self):
+        load_path = os.path.join(BASE_RUN_DIR, self.run_name, "state.pt")
+        if os.path.isfile(load_path):
+            prog = torch.load(load_path, map_location="cuda")
+            self.e = prog["epochs_done"]
+            self.b = prog["batches_done"]
+            self.model.load_state_dict(prog["model_state"])
+            self.optimizer.load_state_dict(prog["optimizer_state"])
+            print(f"Loaded existing model from {load_path}.")
+
+    def save_model(self):
+        prog = {"epochs_done": self.e, "batches_done": self.b,
+                "model_state": self.model.state_dict(), "optimizer_state": self.optimizer.state_dict()}
+        torch.save(prog, os.path.join(BASE_RUN_DIR, self.run_name, "state.pt"))
+
+
+def save_embeddings(trainer, dataset, base_run_dir=BASE_RUN_DIR, override_run_name=None):
+    """Embed all tracks in 256-row batches and save one `<track_id>.pt` (1-D float32 [out])
+    per track, skipping existing files (pinsage_training.py:297-327)."""
+    track_ids = list(dataset.tracks)
+    n = len(track_ids)
+    bsize = 256
+    run_name = override_run_name if override_run_name else trainer.run_name
+    emb_dir = os.path.join(base_run_dir, run_name, "emb")
+    os.makedirs(emb_dir, exist_ok=True)
+    pbar = tqdm(total=n, desc="Saving embeddings")
+    for i in range(0, n, bsize):
+        ids = torch.arange(i, min(i + bsize, n))
+        emb = trainer.embed(ids)
+        for id in ids:
+            save_path = os.path.join(emb_dir, track_ids[id] + ".pt")
+            if os.path.isfile(save_path):
+                continue
+            torch.save(emb[id - i, :].clone().detach(), save_path)
+        pbar.update(bsize)
+    pbar.close()
+
+
+def load_embeddings(trainer, dataset, base_run_dir=BASE_RUN_DIR):
+    """Stack the saved per-track embeddings (pinsage_training.py:330-339)."""
+    emb_dir = os.path.join(base_run_dir, trainer.run_name, "emb")
+    return torch.stack([torch.load(os.path.join(emb_dir, t + ".pt")) for t in dataset.tracks], dim=0)
+
+
+def train_and_save(dataset, track_ids, trainer):
+    """pinsage_training.py:443-450 (without the eyeball kNN print)."""
+    trainer.train()
+    save_embeddings(trainer, dataset)
+    return load_embeddings(trainer, dataset)

@@ -1,0 +1,249 @@
+"""ctypes binding of libpinsage_b200.so (C ABI declared in include/pinsage_b200.h).
+
+There is deliberately NO fallback: if the shared library is missing or a CUDA device is
+not available, every entry point raises.  PyTorch is used only for device memory and
+streams; no torch type crosses the ABI (raw device pointers, sizes and a cudaStream_t).
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import c_char_p, c_double, c_float, c_int, c_int64, c_uint64, c_void_p
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libpinsage_b200.so")
+
+_lib = None
+_device_set = None
+
+
+class NativeError(RuntimeError):
+    pass
+
+
+_SIGNATURES = {
+    "ps_version": ([], c_int),
+    "ps_last_error": ([], c_char_p),
+    "ps_set_device": ([c_int], c_int),
+    "ps_graph_create": ([c_void_p, c_void_p, c_int64, c_int64, c_int64, ctypes.POINTER(c_void_p), c_void_p], c_int),
+    "ps_graph_destroy": ([c_void_p], c_int),
+    "ps_walk_topt": ([c_void_p, c_void_p, c_int64, c_int, c_double, c_int, c_int, c_uint64,
+                      c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p], c_int),
+    "ps_trace_topt": ([c_void_p, c_void_p, c_int64, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p], c_int),
+    "ps_gemm": ([c_void_p, c_int64, c_int, c_void_p, c_void_p, c_int64, c_int, c_void_p, c_void_p, c_int64,
+                 c_int64, c_int64, c_int64, c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_void_p], c_int),
+    "ps_aggregate_fwd": ([c_void_p, c_int64, c_void_p, c_int, c_void_p, c_int64, c_void_p, c_void_p, c_int, c_int,
+                          c_int64, c_void_p, c_int64, c_void_p, c_void_p], c_int),
+    "ps_aggregate_bwd": ([c_void_p, c_int64, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int,
+                          c_void_p, c_int64, c_int64, c_void_p], c_int),
+    "ps_norm_leaky_bwd": ([c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_int64, c_int, c_void_p], c_int),
+    "ps_l2norm_rows": ([c_void_p, c_int64, c_int64, c_int, c_void_p, c_void_p], c_int),
+    "ps_leaky_bwd": ([c_void_p, c_void_p, c_int64, c_void_p], c_int),
+    "ps_colsum": ([c_void_p, c_int64, c_int64, c_int, c_void_p, c_void_p], c_int),
+    "ps_scatter_add_rows": ([c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_int64, c_int, c_void_p], c_int),
+    "ps_count_triples": ([c_void_p, c_int64, c_int64, c_void_p, c_void_p], c_int),
+    "ps_margin_loss_fwd_bwd": ([c_void_p, c_int64, c_void_p, c_int64, c_int, c_float, c_float, c_void_p, c_int64,
+                                c_void_p, c_void_p, c_int64, c_void_p], c_int),
+    "ps_adam_step": ([c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_float, c_float, c_float, c_float, c_int64,
+                      c_float, c_void_p], c_int),
+}
+
+EXPORTED_SYMBOLS = tuple(_SIGNATURES)
+
+
+def load_library(path: str = LIB_PATH):
+    """dlopen the library and declare every prototype (no device needed)."""
+    if not os.path.isfile(path):
+        raise NativeError(
+            f"{path} is missing: build it with `python __graft_entry__.py build` "
+            "(nvcc -gencode arch=compute_100a,code=sm_100a). There is no CPU fallback.")
+    lib = ctypes.CDLL(path)
+    for name, (argtypes, restype) in _SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError if a declared symbol is not exported
+        fn.argtypes = argtypes
+        fn.restype = restype
+    return lib
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        _lib = load_library()
+        if _lib.ps_version() != 1:
+            raise NativeError("libpinsage_b200.so ABI version mismatch")
+    return _lib
+
+
+def _ensure_device():
+    """The library links its own CUDA runtime; point it at torch's current device."""
+    global _device_set
+    if not torch.cuda.is_available():
+        raise NativeError("no CUDA device: the PinSage engine has no CPU fallback")
+    dev = torch.cuda.current_device()
+    if _device_set != dev:
+        check(lib().ps_set_device(dev))
+        _device_set = dev
+    return dev
+
+
+def check(rc: int):
+    if rc != 0:
+        raise NativeError(f"libpinsage_b200 error {rc}: {lib().ps_last_error().decode()}")
+
+
+def _p(t, dtype=None):
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise NativeError("expected a CUDA tensor")
+    if dtype is not None and t.dtype != dtype:
+        raise NativeError(f"expected dtype {dtype}, got {t.dtype}")
+    if not t.is_contiguous() and t.dim() > 1 and t.stride(-1) != 1:
+        raise NativeError("innermost dimension must be contiguous")
+    return c_void_p(t.data_ptr())
+
+
+launch_count = 0  # kernel-launching ABI calls made so far (bench.py reports the per-step delta)
+
+
+def _stream():
+    global launch_count
+    launch_count += 1
+    return c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ld(t):
+    return t.stride(0) if t.dim() == 2 else t.numel()
+
+
+# ------------------------------------------------------------------------------------
+# graph + walker
+# ------------------------------------------------------------------------------------
+
+class GraphHandle:
+    """Owns the device CSR tensors and the opaque ps_graph_t*."""
+
+    def __init__(self, indptr: torch.Tensor, indices: torch.Tensor, n_tracks: int, n_cols: int):
+        _ensure_device()
+        self.indptr = indptr.to(device="cuda", dtype=torch.int64).contiguous()
+        self.indices = indices.to(device="cuda", dtype=torch.int32).contiguous()
+        self.n_tracks, self.n_cols = int(n_tracks), int(n_cols)
+        if self.indptr.numel() != n_tracks + n_cols + 1:
+            raise NativeError("indptr must have n_tracks + n_cols + 1 entries")
+        handle = c_void_p()
+        check(lib().ps_graph_create(_p(self.indptr), _p(self.indices), self.n_tracks, self.n_cols,
+                                    self.indices.numel(), ctypes.byref(handle), _stream()))
+        self._h = handle
+
+    def __del__(self):
+        h, self._h = getattr(self, "_h", None), None
+        if h and _lib is not None:
+            _lib.ps_graph_destroy(h)
+
+
+def walk_topt(graph: GraphHandle, sources: torch.Tensor, n_hops: int, alpha: float, T: int, seed: int,
+              fixed_len: int = 0, want_i64: bool = True, want_i32: bool = False, want_trace: bool = False):
+    """ps_walk_topt.  Returns dict with the requested outputs."""
+    _ensure_device()
+    src = sources.to(device="cuda", dtype=torch.int64).contiguous()
+    n = src.numel()
+    out = {}
+    if want_i64:
+        out["nodes"] = torch.empty((n, T), dtype=torch.int64, device="cuda")
+        out["weights"] = torch.empty((n, T), dtype=torch.float64, device="cuda")
+    if want_i32:
+        out["nodes_i32"] = torch.empty((n, T), dtype=torch.int32, device="cuda")
+        out["weights_f32"] = torch.empty((n, T), dtype=torch.float32, device="cuda")
+    if want_trace:
+        out["trace"] = torch.empty((n, n_hops), dtype=torch.int32, device="cuda")
+    check(lib().ps_walk_topt(graph._h, _p(src), n, int(n_hops), float(alpha), int(fixed_len), int(T),
+                             int(seed) & 0xFFFFFFFFFFFFFFFF,
+                             _p(out.get("nodes")), _p(out.get("weights")), _p(out.get("nodes_i32")),
+                             _p(out.get("weights_f32")), _p(out.get("trace")), _stream()))
+    return out
+
+
+def trace_topt(trace: torch.Tensor, sources: torch.Tensor, T: int):
+    """ps_trace_topt on a caller-supplied int64 trace [n, n_hops]."""
+    _ensure_device()
+    tr = trace.to(device="cuda", dtype=torch.int64).contiguous()
+    src = sources.to(device="cuda", dtype=torch.int64).contiguous()
+    n, n_hops = tr.shape
+    nodes = torch.empty((n, T), dtype=torch.int64, device="cuda")
+    w = torch.empty((n, T), dtype=torch.float64, device="cuda")
+    check(lib().ps_trace_topt(_p(tr), _p(src), n, n_hops, int(T), _p(nodes), _p(w), None, None, _stream()))
+    return w, nodes
+
+
+# ------------------------------------------------------------------------------------
+# dense + row-wise kernels
+# ------------------------------------------------------------------------------------
+
+def gemm(P, Q, C, M, N, K, *, p_kmajor=True, q_kmajor=True, p_rows=None, q_rows=None, bias=None,
+         act=0, l2norm=False, norm_out=None, accumulate=False, splits=1):
+    """C[i,j] (+)= act(sum_r P(i,r) Q(j,r) + bias[j]); see ps_gemm in the header."""
+    check(lib().ps_gemm(_p(P, torch.float32), _ld(P), int(p_kmajor), _p(p_rows, torch.int32),
+                        _p(Q, torch.float32), _ld(Q), int(q_kmajor), _p(q_rows, torch.int32),
+                        _p(C, torch.float32), _ld(C), int(M), int(N), int(K), _p(bias, torch.float32),
+                        int(act), int(l2norm), _p(norm_out, torch.float32), int(accumulate), int(splits), _stream()))
+
+
+def aggregate_fwd(hin, self_rows, din, z, nbz, nbw, dh, cat, inv_wsum):
+    n, T = nbz.shape
+    check(lib().ps_aggregate_fwd(_p(hin, torch.float32), _ld(hin), _p(self_rows, torch.int32), int(din),
+                                 _p(z, torch.float32), _ld(z), _p(nbz, torch.int32), _p(nbw, torch.float32),
+                                 int(T), int(dh), int(n), _p(cat, torch.float32), _ld(cat),
+                                 _p(inv_wsum, torch.float32), _stream()))
+
+
+def aggregate_bwd(dcat, col_off, dh, seg_off, pair_q, nbw, inv_wsum, T, z):
+    check(lib().ps_aggregate_bwd(_p(dcat, torch.float32), _ld(dcat), int(col_off), int(dh),
+                                 _p(seg_off, torch.int32), _p(pair_q, torch.int32), _p(nbw, torch.float32),
+                                 _p(inv_wsum, torch.float32), int(T), _p(z, torch.float32), _ld(z),
+                                 int(z.shape[0]), _stream()))
+
+
+def norm_leaky_bwd(h, norm, dh, dpre):
+    n, d = h.shape
+    check(lib().ps_norm_leaky_bwd(_p(h, torch.float32), _ld(h), _p(norm, torch.float32), _p(dh, torch.float32), _ld(dh),
+                                  _p(dpre, torch.float32), _ld(dpre), int(n), int(d), _stream()))
+
+
+def l2norm_rows(x, norm_out):
+    n, d = x.shape
+    check(lib().ps_l2norm_rows(_p(x, torch.float32), _ld(x), int(n), int(d), _p(norm_out, torch.float32), _stream()))
+
+
+def leaky_bwd(y, dy):
+    assert y.is_contiguous() and dy.is_contiguous()
+    check(lib().ps_leaky_bwd(_p(y, torch.float32), _p(dy, torch.float32), int(y.numel()), _stream()))
+
+
+def colsum(x, out):
+    n, d = x.shape
+    check(lib().ps_colsum(_p(x, torch.float32), _ld(x), int(n), int(d), _p(out, torch.float32), _stream()))
+
+
+def scatter_add_rows(src, rows, dst, d):
+    check(lib().ps_scatter_add_rows(_p(src, torch.float32), _ld(src), _p(rows, torch.int32), _p(dst, torch.float32),
+                                    _ld(dst), int(src.shape[0]), int(d), _stream()))
+
+
+def count_triples(triples, U, dup_counts):
+    check(lib().ps_count_triples(_p(triples, torch.int32), int(triples.shape[0]), int(U), _p(dup_counts, torch.int32), _stream()))
+
+
+def margin_loss_fwd_bwd(emb, triples, margin, grad_scale, dup_counts, loss_out, demb):
+    U, d = emb.shape
+    check(lib().ps_margin_loss_fwd_bwd(_p(emb, torch.float32), _ld(emb), _p(triples, torch.int32), int(triples.shape[0]),
+                                       int(d), float(margin), float(grad_scale), _p(dup_counts, torch.int32), int(U),
+                                       _p(loss_out, torch.float32), _p(demb, torch.float32),
+                                       _ld(demb) if demb is not None else 0, _stream()))
+
+
+def adam_step(param, grad, exp_avg, exp_avg_sq, lr, beta1, beta2, eps, step, grad_scale=1.0):
+    check(lib().ps_adam_step(_p(param, torch.float32), _p(grad, torch.float32), _p(exp_avg, torch.float32),
+                             _p(exp_avg_sq, torch.float32), int(param.numel()), float(lr), float(beta1), float(beta2),
+                             float(eps), int(step), float(grad_scale), _stream()))

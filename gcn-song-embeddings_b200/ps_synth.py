@@ -1,0 +1,78 @@
+"""Synthetic track-collection datasets in the shapes BASELINE.json names (the reference's
+own datasets are not in its checkout).  Pure torch index
+work, device-agnostic: small graphs on the CPU for tests, the 1 M / 200 k / 40 M bench
+graph directly in HBM.
+"""
+from __future__ import annotations
+
+import torch
+
+import ps_native
+from ps_graph import PSGraph
+
+
+def bipartite_csr(n_tracks: int, n_cols: int, n_edges: int, seed: int = 1234, device="cpu",
+                  max_col_size: int = 5000, skew: float = 2.0):
+    """Bipartite graph with Zipf-like collection sizes (shape 1.2, clipped to
+    [2, max_col_size], scaled to ~n_edges memberships) and popularity-skewed track
+    endpoints; duplicate memberships removed; every node has degree >= 1.
+    Returns (indptr int64 [N+C+1], indices int32 [2E'], E')."""
+    gen = torch.Generator(device=device).manual_seed(seed)
+    u = torch.rand(n_cols, generator=gen, device=device, dtype=torch.float64)
+    raw = (1.0 - u).clamp_min(1e-12).pow(-1.0 / 1.2)
+    cap = min(max_col_size, n_tracks)
+    sizes = (raw * (n_edges / raw.sum())).round().clamp(2, cap)
+    # one rescale pass after clipping so the total lands near n_edges
+    sizes = (sizes * (n_edges / sizes.sum())).round().clamp(2, cap).to(torch.int64)
+    col = torch.repeat_interleave(torch.arange(n_cols, device=device), sizes)
+    ut = torch.rand(col.numel(), generator=gen, device=device, dtype=torch.float64)
+    relabel = torch.randperm(n_tracks, generator=gen, device=device)  # popular tracks scattered over the id space
+    track = relabel[(ut.pow(skew) * n_tracks).to(torch.int64).clamp_max(n_tracks - 1)]
+    # every track at least once
+    missing = torch.ones(n_tracks, dtype=torch.bool, device=device)
+    missing[track] = False
+    miss = missing.nonzero().flatten()
+    if miss.numel():
+        track = torch.cat([track, miss])
+        col = torch.cat([col, torch.randint(0, n_cols, (miss.numel(),), generator=gen, device=device)])
+    key = torch.unique(col * n_tracks + track)
+    col, track = key // n_tracks, key % n_tracks
+    e = key.numel()
+    src = torch.cat([track, col + n_tracks])
+    dst = torch.cat([col + n_tracks, track])
+    order = torch.argsort(src, stable=True)
+    n = n_tracks + n_cols
+    indptr = torch.zeros(n + 1, dtype=torch.int64, device=device)
+    indptr[1:] = torch.cumsum(torch.bincount(src, minlength=n), 0)
+    return indptr, dst[order].to(torch.int32), e
+
+
+def make_graph(n_tracks, n_cols, n_edges, seed=1234, device="cpu", **kw) -> PSGraph:
+    indptr, indices, _ = bipartite_csr(n_tracks, n_cols, n_edges, seed, device, **kw)
+    g = PSGraph(indptr.cpu(), indices.cpu(), n_tracks, n_cols)
+    if indptr.is_cuda:  # keep the device copy instead of uploading again
+        g._handle = ps_native.GraphHandle(indptr, indices, n_tracks, n_cols)
+    return g
+
+
+def features(n_tracks, dim, seed=1, device="cpu"):
+    """N(0,1) features standardised per column like SpotifyGraph.to_dgl_graph
+    (spotify_graph.py:77-79)."""
+    gen = torch.Generator(device=device).manual_seed(seed)
+    x = torch.randn((n_tracks, dim), generator=gen, device=device, dtype=torch.float32)
+    return (x - x.mean(0)) / (x.std(0, unbiased=True) + 1e-12)
+
+
+def cooccurrence_positives(indptr, indices, n_tracks, n_pairs, seed=2):
+    """Random (a, b) track pairs that share a collection (2-step co-occurrence), a != b."""
+    device = indptr.device
+    gen = torch.Generator(device=device).manual_seed(seed)
+    track_entries = int(indptr[n_tracks])
+    e = torch.randint(0, track_entries, (n_pairs,), generator=gen, device=device)
+    a = torch.searchsorted(indptr[: n_tracks + 1], e, right=True) - 1
+    c = indices[e].to(torch.int64)
+    deg = indptr[c + 1] - indptr[c]
+    r = (torch.rand(n_pairs, generator=gen, device=device, dtype=torch.float64) * deg).to(torch.int64).clamp_max(deg - 1)
+    b = indices[indptr[c] + r].to(torch.int64)
+    keep = a != b
+    return torch.stack([a[keep], b[keep]], 1)

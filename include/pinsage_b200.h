@@ -1,0 +1,136 @@
+/*
+ * pinsage_b200.h -- C ABI of libpinsage_b200.so, the B200 (sm_100a) engine behind the
+ * PinSage hot path of MatejBevec/gcn-song-embeddings.
+ *
+ * The reference is pure Python and has no FFI layer of its own, so
+ * each entry point below cites the reference function (file:line under /root/reference)
+ * whose arithmetic it replaces.  INTEGRATION.md shows the ctypes stubs a maintainer of
+ * the reference would add.
+ *
+ * Conventions
+ *   - every function returns 0 on success or a negative PS_ERR_* code; the message is
+ *     available from ps_last_error() (thread-local);
+ *   - all pointers are DEVICE pointers owned by the caller unless stated otherwise; the
+ *     library never allocates device memory behind the caller's back (ps_graph_t keeps
+ *     the caller's CSR pointers, it does not copy them);
+ *   - every launch is asynchronous on `stream` (a cudaStream_t passed as void*);
+ *   - row-major matrices with an explicit leading dimension in ELEMENTS;
+ *   - no global state; one host thread per device.
+ */
+#ifndef PINSAGE_B200_H
+#define PINSAGE_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PS_ABI_VERSION 1
+
+typedef struct ps_graph ps_graph_t;
+typedef void* ps_stream_t; /* cudaStream_t */
+
+int ps_version(void);
+const char* ps_last_error(void);
+/* Select the CUDA device for the calling host thread (call once per process/thread). */
+int ps_set_device(int device);
+
+/* ---- graph: adjacency lookup that replaces DGL (pinsage_model.py:41,44,93;
+ *      spotify_graph.py:48-63).  Nodes [0, n_tracks) are tracks, [n_tracks,
+ *      n_tracks+n_cols) collections; CSR over all of them, multi-edges kept.
+ *      Fails with PS_ERR_GRAPH if any node has no successors (the reference's
+ *      torch.randint(0) raises there, pinsage_model.py:42). Synchronises `stream`. ---- */
+int ps_graph_create(const int64_t* indptr, const int32_t* indices, int64_t n_tracks, int64_t n_cols,
+                    int64_t n_entries, ps_graph_t** out, ps_stream_t stream);
+int ps_graph_destroy(ps_graph_t* g);
+
+/* ---- K1+K2: restart random walks fused with the visit-count top-T reduction.
+ *      Replaces do_random_walks + sample_neighborhood + sample_neighborhood_topt
+ *      (pinsage_model.py:32-53, 88-107).  One warp per source; draws keyed by
+ *      Philox4x32-10(counter=(step, source, 0, 0), key=seed).  fixed_len > 0 = restart
+ *      deterministically every fixed_len steps (BASELINE.json config 5) instead of the
+ *      alpha draw.  Any output pointer may be NULL.  Outputs are ordered by (count desc,
+ *      node id asc); slots beyond the number of distinct visited nodes carry weight 0 and
+ *      the source id.  weights = count / n_hops (IEEE double divide). ---- */
+int ps_walk_topt(const ps_graph_t* g, const int64_t* sources, int64_t n, int n_hops, double alpha,
+                 int fixed_len, int T, uint64_t seed,
+                 int64_t* out_nodes_i64, double* out_w_f64, int32_t* out_nodes_i32, float* out_w_f32,
+                 int32_t* out_trace, ps_stream_t stream);
+/* K2 alone on a caller-supplied trace [n, n_hops] (bit-exact parity hook against
+ * sample_neighborhood_topt fed the same trace, pinsage_model.py:96-99,107). */
+int ps_trace_topt(const int64_t* trace, const int64_t* sources, int64_t n, int n_hops, int T,
+                  int64_t* out_nodes_i64, double* out_w_f64, int32_t* out_nodes_i32, float* out_w_f32,
+                  ps_stream_t stream);
+
+/* ---- K5/K7/K9 and their backward: the dense contraction
+ *        C[i, j] (+)= act( sum_{r<K} P(i, r) * Q(j, r) + bias[j] )
+ *      P(i, r) = p_kmajor ? P[prow(i)*ldp + r] : P[prow(r)*ldp + i]   (same for Q),
+ *      prow(x) = p_rows ? p_rows[x] : x  (row gather folded into the operand load, K4).
+ *      act: 0 none, 1 leaky_relu(0.01).  l2norm: divide each output row by its L2 norm
+ *      (requires N <= 128; norm_out[i] receives the norm, may be NULL).
+ *      accumulate: atomically add into C instead of storing (bias/act/l2norm must be off);
+ *      splits > 1 partitions K over CTAs (needs accumulate).
+ *      Replaces nn.Linear + leaky_relu + row normalise in ConvLayer.forward and the head
+ *      (pinsage_model.py:201,208-210,259) and autograd's AddmmBackward. ---- */
+int ps_gemm(const float* P, int64_t ldp, int p_kmajor, const int32_t* p_rows,
+            const float* Q, int64_t ldq, int q_kmajor, const int32_t* q_rows,
+            float* C, int64_t ldc, int64_t M, int64_t N, int64_t K,
+            const float* bias, int act, int l2norm, float* norm_out, int accumulate, int splits,
+            ps_stream_t stream);
+
+/* ---- K4+K6: neighbour gather + importance-weighted mean fused with the concat
+ *      (pinsage_model.py:195-197,202,208):
+ *        cat[i, 0:din]       = hin[self_rows[i], 0:din]
+ *        cat[i, din:din+dh]  = sum_t nbw[i,t] * z[nbz[i,t], 0:dh] / sum_t nbw[i,t]
+ *      inv_wsum[i] = 1 / sum_t nbw[i,t] is saved for the backward. ---- */
+int ps_aggregate_fwd(const float* hin, int64_t ld_hin, const int32_t* self_rows, int din,
+                     const float* z, int64_t ldz, const int32_t* nbz, const float* nbw, int T, int dh,
+                     int64_t n, float* cat, int64_t ldcat, float* inv_wsum, ps_stream_t stream);
+/* ---- K11: backward of the aggregation as a segmented gather (no atomics).  For z-row u
+ *      with incoming (target, slot) pairs pair_q[seg_off[u] .. seg_off[u+1]) (q = i*T + t):
+ *        z[u, :] = leaky'(z[u, :]) * sum_q nbw[q] * inv_wsum[q / T] * dcat[q / T, col_off : col_off+dh]
+ *      (z holds leaky_relu outputs on entry and d(pre-activation) on exit). ---- */
+int ps_aggregate_bwd(const float* dcat, int64_t ldcat, int col_off, int dh,
+                     const int32_t* seg_off, const int32_t* pair_q, const float* nbw,
+                     const float* inv_wsum, int T, float* z, int64_t ldz, int64_t n_zrows,
+                     ps_stream_t stream);
+/* backward of  h = y / ||y||,  y = leaky_relu(pre)  (pinsage_model.py:209-210):
+ *   dpre = leaky'(h) * (dh - h * (h . dh)) / norm */
+int ps_norm_leaky_bwd(const float* h, int64_t ldh, const float* norm, const float* dh, int64_t lddh,
+                      float* dpre, int64_t ldp, int64_t n, int d, ps_stream_t stream);
+/* x[i,:] /= ||x[i,:]||, norm_out[i] = the norm (row normalise of pinsage_model.py:210 when out_dim > 128). */
+int ps_l2norm_rows(float* x, int64_t ld, int64_t n, int d, float* norm_out, ps_stream_t stream);
+/* dy[i] *= leaky'(y[i]) elementwise (y = leaky_relu output). */
+int ps_leaky_bwd(const float* y, float* dy, int64_t n_elems, ps_stream_t stream);
+/* out[j] += sum_i x[i*ld + j]  (bias gradients). */
+int ps_colsum(const float* x, int64_t ld, int64_t n, int d, float* out, ps_stream_t stream);
+/* dst[rows[i], 0:d] += src[i, 0:d]; rows must be unique (self-row gradient). */
+int ps_scatter_add_rows(const float* src, int64_t lds, const int32_t* rows, float* dst, int64_t ldd,
+                        int64_t n, int d, ps_stream_t stream);
+
+/* ---- K10: max-margin loss forward + backward with the (q, pos, neg) gather and the
+ *      gradient scatter-add fused (pinsage_training.py:31-41, 184-190).
+ *      emb [U, d] holds one embedding per DISTINCT batch node; triples [B, 3] index rows
+ *      of emb.  loss_out[0] += mean_b max(q^.n^ - q^.p^ + margin, 0)  (x^ = F.normalize,
+ *      eps 1e-12).  demb [U, d] += d loss / d emb, where the contribution of a node that
+ *      occurs k times in one column is additionally multiplied by k when dup_counts
+ *      ([3, U] occurrence counts per column, from ps_count_triples) is non-NULL: that is
+ *      the reference's duplicate-nodeset gradient factor (pinsage_model.py:260,265;
+ *      SURVEY.md section 0 item 8).  grad_scale multiplies every gradient. ---- */
+int ps_count_triples(const int32_t* triples, int64_t B, int64_t U, int32_t* dup_counts, ps_stream_t stream);
+int ps_margin_loss_fwd_bwd(const float* emb, int64_t ld, const int32_t* triples, int64_t B, int d,
+                           float margin, float grad_scale, const int32_t* dup_counts, int64_t U,
+                           float* loss_out, float* demb, int64_t ldd, ps_stream_t stream);
+
+/* ---- K13: Adam step on a flat fp32 parameter buffer (torch.optim.Adam defaults:
+ *      betas, eps, no weight decay, no amsgrad; pinsage_training.py:147,191).
+ *      step is the 1-based step count used for bias correction. ---- */
+int ps_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n,
+                 float lr, float beta1, float beta2, float eps, int64_t step, float grad_scale,
+                 ps_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PINSAGE_B200_H */

@@ -1,0 +1,191 @@
+"""GPU parity tests of the dense / row-wise kernels through the C ABI, each against a
+plain fp32/fp64 torch statement of the same op."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-4
+
+
+@pytest.fixture(scope="module")
+def nat():
+    import ps_native
+    return ps_native
+
+
+def rel(a, b):
+    a, b = a.double(), b.double()
+    return float((a - b).norm() / b.norm().clamp_min(1e-30))
+
+
+def leaky(x):
+    return torch.nn.functional.leaky_relu(x, 0.01)
+
+
+@pytest.mark.parametrize("M,N,K", [(1, 4, 4), (130, 36, 20), (257, 128, 64), (1000, 512, 256), (4096, 132, 772)])
+@pytest.mark.parametrize("pk,qk", [(True, True), (True, False), (False, True), (False, False)])
+def test_gemm_layouts(nat, M, N, K, pk, qk):
+    torch.manual_seed(M * 7 + N)
+    if not pk and M % 4:
+        M = (M + 3) // 4 * 4
+    A = torch.randn(M, K, device="cuda"); B = torch.randn(N, K, device="cuda")
+    P = A.contiguous() if pk else A.t().contiguous()
+    Q = B.contiguous() if qk else B.t().contiguous()
+    C = torch.empty(M, N, device="cuda")
+    nat.gemm(P, Q, C, M, N, K, p_kmajor=pk, q_kmajor=qk)
+    want = (A.double() @ B.double().t())
+    assert rel(C, want) < 1e-5
+
+
+def test_gemm_gather_bias_act_norm(nat):
+    torch.manual_seed(1)
+    table = torch.randn(5000, 256, device="cuda")
+    rows = torch.randint(0, 5000, (777,), device="cuda", dtype=torch.int32)
+    W = torch.randn(128, 256, device="cuda") * 0.1; b = torch.randn(128, device="cuda")
+    out = torch.empty(777, 128, device="cuda"); norm = torch.empty(777, device="cuda")
+    nat.gemm(table, W, out, 777, 128, 256, p_rows=rows, bias=b, act=1, l2norm=True, norm_out=norm)
+    y = leaky(table[rows.long()].double() @ W.double().t() + b.double())
+    assert rel(norm, y.norm(dim=1)) < 1e-5
+    assert rel(out, y / y.norm(dim=1, keepdim=True)) < 1e-5
+    # narrow output (N < tile) with the norm epilogue
+    W2 = torch.randn(32, 256, device="cuda") * 0.1
+    out2 = torch.empty(777, 32, device="cuda")
+    nat.gemm(table, W2, out2, 777, 32, 256, p_rows=rows, act=1, l2norm=True)
+    y2 = leaky(table[rows.long()].double() @ W2.double().t())
+    assert rel(out2, y2 / y2.norm(dim=1, keepdim=True)) < 1e-5
+
+
+@pytest.mark.parametrize("splits", [1, 7, 64])
+def test_gemm_wgrad_accumulate(nat, splits):
+    """dW[n,k] += sum_m dY[m,n] X[rows[m],k]  (both operands MN-major, gather on the contraction index)."""
+    torch.manual_seed(2)
+    m = 10_000
+    dY = torch.randn(m, 96, device="cuda"); X = torch.randn(3000, 64, device="cuda")
+    rows = torch.randint(0, 3000, (m,), device="cuda", dtype=torch.int32)
+    dW = torch.ones(96, 64, device="cuda")
+    nat.gemm(dY, X, dW, 96, 64, m, p_kmajor=False, q_kmajor=False, q_rows=rows, accumulate=True, splits=splits)
+    want = 1.0 + dY.double().t() @ X[rows.long()].double()
+    assert rel(dW, want) < 1e-5
+
+
+def test_gemm_rejects_bad_shapes(nat):
+    A = torch.randn(8, 6, device="cuda"); B = torch.randn(4, 6, device="cuda"); C = torch.empty(8, 4, device="cuda")
+    with pytest.raises(nat.NativeError):
+        nat.gemm(A, B, C, 8, 4, 6)  # K, ld not multiples of 4
+
+
+@pytest.mark.parametrize("n,T,din,dh", [(1, 1, 4, 4), (333, 3, 64, 96), (1000, 50, 256, 512), (500, 10, 128, 1024), (64, 7, 32, 132)])
+def test_aggregate_fwd_bwd(nat, n, T, din, dh):
+    torch.manual_seed(n + T)
+    n_in, nz = 2 * n + 5, 3 * n + 7
+    hin = torch.randn(n_in, din, device="cuda")
+    z = leaky(torch.randn(nz, dh, device="cuda"))
+    self_rows = torch.randint(0, n_in, (n,), device="cuda", dtype=torch.int32)
+    nbz = torch.randint(0, nz, (n, T), device="cuda", dtype=torch.int32)
+    w = torch.randint(1, 40, (n, T), device="cuda").float() / 500
+    cat = torch.empty(n, din + dh, device="cuda"); inv = torch.empty(n, device="cuda")
+    nat.aggregate_fwd(hin, self_rows, din, z, nbz, w, dh, cat, inv)
+    agg = (w.double()[:, :, None] * z[nbz.long()].double()).sum(1) / w.double().sum(1, keepdim=True)
+    assert torch.equal(cat[:, :din], hin[self_rows.long()])
+    assert rel(cat[:, din:], agg) < 1e-6
+    assert rel(inv, 1 / w.double().sum(1)) < 1e-6
+    # backward: dZ[u] = leaky'(z[u]) * sum_{(i,t): nbz=u} w/wsum * dcat[i, din:]
+    dcat = torch.randn(n, din + dh, device="cuda")
+    flat = nbz.reshape(-1)
+    _, order = torch.sort(flat)
+    seg = torch.zeros(nz + 1, dtype=torch.int32, device="cuda")
+    seg[1:] = torch.cumsum(torch.bincount(flat, minlength=nz), 0)
+    zz = z.clone()
+    nat.aggregate_bwd(dcat, din, dh, seg, order.to(torch.int32), w, inv, T, zz)
+    coef = (w.double() / w.double().sum(1, keepdim=True)).reshape(-1)
+    contrib = coef[:, None] * dcat[:, din:].double().repeat_interleave(T, 0)
+    want = torch.zeros(nz, dh, device="cuda", dtype=torch.float64).index_add_(0, flat.long(), contrib)
+    want = want * torch.where(z > 0, 1.0, 0.01).double()
+    assert rel(zz, want) < 1e-5
+
+
+def test_rowwise_kernels(nat):
+    torch.manual_seed(3)
+    n, d = 1234, 128
+    pre = torch.randn(n, d, device="cuda", dtype=torch.float64, requires_grad=True)
+    y = leaky(pre); h = y / y.norm(dim=1, keepdim=True)
+    g = torch.randn(n, d, device="cuda", dtype=torch.float64)
+    (h * g).sum().backward()
+    dpre = torch.empty(n, d, device="cuda")
+    nat.norm_leaky_bwd(h.detach().float(), y.detach().norm(dim=1).float(), g.float(), dpre)
+    assert rel(dpre, pre.grad) < 1e-5
+    # leaky_bwd
+    yy = leaky(torch.randn(n, d, device="cuda")); dy = torch.randn(n, d, device="cuda"); ref = dy * torch.where(yy > 0, 1.0, 0.01)
+    nat.leaky_bwd(yy, dy)
+    assert torch.allclose(dy, ref)
+    # colsum (accumulating)
+    x = torch.randn(5001, 772, device="cuda"); out = torch.ones(772, device="cuda")
+    nat.colsum(x, out)
+    assert rel(out, 1 + x.double().sum(0)) < 1e-5
+    # scatter_add_rows into a strided source view
+    src = torch.randn(300, 200, device="cuda"); dst = torch.randn(1000, 64, device="cuda"); ref = dst.clone()
+    rows = torch.randperm(1000, device="cuda")[:300].to(torch.int32)
+    ref[rows.long()] += src[:, :64]
+    nat.scatter_add_rows(src, rows, dst, 64)
+    assert torch.allclose(dst, ref)
+    # l2norm_rows
+    x = torch.randn(77, 512, device="cuda"); ref = x / x.norm(dim=1, keepdim=True); nrm = torch.empty(77, device="cuda")
+    nat.l2norm_rows(x, nrm)
+    assert rel(x, ref) < 1e-6
+
+
+@pytest.mark.parametrize("tag", ["a", "b", "c", "d"])
+def test_margin_loss_vs_reference(nat, golden, tag):
+    """K10 against the reference's max_margin_loss values and autograd gradients."""
+    g = golden("loss")
+    q, p, n = (torch.tensor(g[f"{tag}_{nm}"], device="cuda") for nm in "qpn")
+    B, d = q.shape
+    emb = torch.cat([q, p, n], 0).contiguous()
+    idx = torch.arange(B, device="cuda", dtype=torch.int32)
+    triples = torch.stack([idx, idx + B, idx + 2 * B], 1).contiguous()
+    loss = torch.zeros(1, device="cuda"); demb = torch.zeros_like(emb)
+    nat.margin_loss_fwd_bwd(emb, triples, float(g[f"{tag}_margin"]), 1.0, None, loss, demb)
+    assert abs(float(loss) - float(g[f"{tag}_loss"])) <= 1e-5 * max(1.0, abs(float(g[f"{tag}_loss"])))
+    want = torch.tensor(np.concatenate([g[f"{tag}_dq"], g[f"{tag}_dp"], g[f"{tag}_dn"]]), device="cuda")
+    assert rel(demb, want) < RTOL
+
+
+def test_margin_loss_shared_rows_and_dup_factor(nat):
+    """Triples that index shared embedding rows; duplicate counts multiply the gradient."""
+    torch.manual_seed(5)
+    U, d, B = 40, 64, 64
+    emb = torch.randn(U, d, device="cuda", dtype=torch.float64, requires_grad=True)
+    triples = torch.randint(0, U, (B, 3), device="cuda")
+    counts = torch.empty(3, U, dtype=torch.int32, device="cuda")
+    nat.count_triples(triples.to(torch.int32), U, counts)
+    for j in range(3):
+        assert torch.equal(counts[j].long(), torch.bincount(triples[:, j], minlength=U))
+    norm = torch.nn.functional.normalize
+    hq, hp, hn = (norm(emb[triples[:, j]], dim=1) for j in range(3))
+    dsum = (hq * hn).sum(1) - (hq * hp).sum(1) + 0.1
+    lossv = torch.clamp(dsum, min=0).mean()
+    # reference-compat gradient: each occurrence scaled by its column count
+    gq, gp, gn = torch.autograd.grad(lossv, [hq, hp, hn], retain_graph=True)
+    rows = []
+    for j, (hx, gx) in enumerate(((hq, gq), (hp, gp), (hn, gn))):
+        k = counts[j].double()[triples[:, j]][:, None]
+        rows.append(torch.autograd.grad(hx, emb, gx * k, retain_graph=True)[0])
+    want = sum(rows)
+    loss = torch.zeros(1, device="cuda"); demb = torch.zeros(U, d, device="cuda")
+    nat.margin_loss_fwd_bwd(emb.detach().float(), triples.to(torch.int32), 0.1, 1.0, counts, loss, demb)
+    assert abs(float(loss) - float(lossv)) < 1e-5
+    assert rel(demb, want) < RTOL
+
+
+def test_adam_matches_torch(nat):
+    torch.manual_seed(6)
+    p = torch.randn(10_001, device="cuda"); ref = torch.nn.Parameter(p.clone())
+    opt = torch.optim.Adam([ref], lr=1e-3)
+    m = torch.zeros_like(p); v = torch.zeros_like(p)
+    for step in range(1, 6):
+        g = torch.randn_like(p)
+        ref.grad = g.clone(); opt.step()
+        nat.adam_step(p, g, m, v, 1e-3, 0.9, 0.999, 1e-8, step)
+    assert torch.allclose(p, ref.data, rtol=1e-5, atol=1e-7)

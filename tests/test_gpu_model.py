@@ -1,0 +1,168 @@
+"""GPU parity of the model path (ConvLayer, PinSageModel forward/backward, fused train
+step, trainer) against golden vectors produced by the unmodified reference and against
+the CPU oracle on fresh random inputs.  Tolerance: 1e-4 relative (north_star)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import oracle
+
+pytestmark = pytest.mark.gpu
+RTOL = 1e-4
+
+
+def rel(a, b):
+    a = torch.as_tensor(np.asarray(a) if not torch.is_tensor(a) else a).double().cpu()
+    b = torch.as_tensor(np.asarray(b) if not torch.is_tensor(b) else b).double().cpu()
+    return float((a - b).norm() / b.norm().clamp_min(1e-30))
+
+
+def _inputs(g):
+    seed, n, dims, L, T = int(g["seed"]), int(g["n"]), tuple(int(x) for x in g["dims"]), int(g["L"]), int(g["T"])
+    rng = np.random.RandomState(seed)
+    features = torch.tensor(rng.standard_normal((n, dims[0])), dtype=torch.float32)
+    params = oracle.make_params(L, dims, np.random.RandomState(seed + 1))
+    nbhds = (torch.from_numpy(g["w"]), torch.from_numpy(g["nodes"]))
+    return features, params, nbhds, n, L, T, dims
+
+
+def _model(n, L, dims, T, nbhds, params):
+    import pinsage_model as psm
+    m = psm.PinSageModel(None, n, L, dims, 500, 0.85, T, nbhds)
+    m.load_state_dict(params)
+    return m
+
+
+@pytest.mark.parametrize("tag", ["small", "l3", "default"])
+def test_forward_and_autograd_vs_reference(golden, tag):
+    import pinsage_model as psm
+    g = golden(f"model_{tag}")
+    features, params, nbhds, n, L, T, dims = _inputs(g)
+    full = tag != "default"
+    model = _model(n, L, dims, T, nbhds, params)
+    batch = torch.from_numpy(g["batch"])
+    # ConvLayer.forward with the reference's signature
+    S = psm.relevant_nodes_per_layer_precomp(batch[:, 0], L, T, nbhds)
+    ns0, w0, nb0 = S[0]
+    c0 = model.conv_layers[0](features, ns0, nb0, w0)
+    assert not c0.is_cuda and rel(c0, g["conv0_out"]) < RTOL
+    # one call + linear functional: embeddings and the duplicate-node gradient factor
+    emb = model(features, batch[:, 0])
+    assert not emb.is_cuda and emb.shape == (batch.shape[0], dims[2])
+    assert rel(emb.detach(), g["emb_q"]) < RTOL
+    (emb * torch.from_numpy(g["R"])).sum().backward()
+    for k, p in model.named_parameters():
+        got = p.grad if full else p.grad.reshape(-1)[::97]
+        assert rel(got, g[f"lin_grad/{k}"]) < RTOL, k
+    # three separate calls + torch loss through autograd (exactly the reference's train_batch graph)
+    import pinsage_training as pst
+    for mtag, margin in (("m1e-5", 1e-5), ("m0.5", 0.5)):
+        model.zero_grad()
+        hq, hp, hn = model(features, batch[:, 0]), model(features, batch[:, 1]), model(features, batch[:, 2])
+        loss = pst.max_margin_loss(hq, hp, hn, margin)
+        loss.backward()
+        assert abs(float(loss) - float(g[f"{mtag}/loss"])) < RTOL * abs(float(g[f"{mtag}/loss"])) + 1e-9
+        assert rel(hp.detach(), g[f"{mtag}/hp"]) < RTOL
+        for k, p in model.named_parameters():
+            got = p.grad if full else p.grad.reshape(-1)[::97]
+            assert rel(got, g[f"{mtag}/grad/{k}"]) < 5 * RTOL, (mtag, k)
+
+
+@pytest.mark.parametrize("tag", ["small", "l3", "default"])
+def test_fused_train_step_vs_reference(golden, tag):
+    """Engine.train_step (shared frontier + CUDA loss/backward) reproduces the reference's
+    loss and parameter gradients, duplicate factor included."""
+    g = golden(f"model_{tag}")
+    features, params, nbhds, n, L, T, dims = _inputs(g)
+    full = tag != "default"
+    model = _model(n, L, dims, T, nbhds, params)
+    feats = model.engine.features(features)
+    batch = torch.from_numpy(g["batch"]).cuda()
+    for mtag, margin in (("m1e-5", 1e-5), ("m0.5", 0.5)):
+        loss, emb, triples = model.engine.train_step(feats, batch, margin, reference_compat=True)
+        assert abs(float(loss) - float(g[f"{mtag}/loss"])) < RTOL * abs(float(g[f"{mtag}/loss"])) + 1e-9
+        assert rel(emb[triples[:, 0].long()], g[f"{mtag}/hq"]) < RTOL
+        assert rel(emb[triples[:, 2].long()], g[f"{mtag}/hn"]) < RTOL
+        for k, p in model.named_parameters():
+            got = p.grad if full else p.grad.reshape(-1)[::97]
+            assert rel(got, g[f"{mtag}/grad/{k}"]) < 5 * RTOL, (mtag, k)
+
+
+def test_trainer_steps_vs_reference(golden, tmp_path, monkeypatch):
+    """Three optimiser steps of the drop-in trainer == the reference trainer's."""
+    import pinsage_training as pst
+    from ps_graph import PSGraph
+    g = golden("train_steps")
+    n, din = int(g["n"]), int(g["din"])
+    rng = np.random.RandomState(21)
+    features = torch.tensor(rng.standard_normal((n, din)), dtype=torch.float32)
+    params = oracle.make_params(2, (din, 512, 128), np.random.RandomState(22))
+    monkeypatch.chdir(tmp_path)
+    nb_path = str(tmp_path / "neighborhoods.pt")
+    torch.save((torch.from_numpy(g["w"]), torch.from_numpy(g["nodes"])), nb_path)
+    graph = PSGraph(np.arange(n + 2), np.r_[np.full(n, n), 0].astype(np.int32), n, 1, nbhds_path=nb_path)
+    positives = torch.from_numpy(rng.randint(0, n, size=(500, 2)).astype(np.int64))
+    trainer = pst.PinSage(graph, n, features, positives, log=False, load_save=False)
+    trainer.model.load_state_dict(params)
+    losses = [float(trainer.train_batch(torch.from_numpy(b))[0]) for b in g["batches"]]
+    assert np.allclose(losses, g["losses"], rtol=2e-3, atol=1e-8)
+    for k, p in trainer.model.named_parameters():
+        assert rel(p.detach().reshape(-1)[::53], g[f"param_sub/{k}"]) < RTOL, k
+    emb = trainer.embed(torch.arange(0, 40))
+    assert not emb.is_cuda and rel(emb, g["emb_after"]) < 1e-3
+    # checkpoint format round trip (state.pt keys of pinsage_training.py:288-295)
+    trainer.save_model()
+    prog = torch.load(os.path.join(pst.BASE_RUN_DIR, trainer.run_name, "state.pt"))
+    assert set(prog) == {"epochs_done", "batches_done", "model_state", "optimizer_state"}
+    assert set(prog["model_state"]) == set(params)
+
+
+def test_frontier_api_vs_reference(golden):
+    import pinsage_model as psm
+    g = golden("frontier")
+    nbhds = (torch.from_numpy(g["w"]), torch.from_numpy(g["nodes"]))
+    for tag, (L, T) in {"L2T3": (2, 3), "L3T5": (3, 5), "L2T10": (2, 10)}.items():
+        S = psm.relevant_nodes_per_layer_precomp(torch.from_numpy(g[f"{tag}_nodeset"]), L, T, nbhds)
+        for l, (ns, w, nb) in enumerate(S):
+            assert np.array_equal(ns.numpy(), g[f"{tag}_ns{l}"]) and np.array_equal(nb.numpy(), g[f"{tag}_nb{l}"])
+            assert np.array_equal(w.numpy().view(np.int64), g[f"{tag}_w{l}"].view(np.int64))
+
+
+@pytest.mark.parametrize("n,dims,L,T,B", [(3000, (256, 512, 128), 2, 10, 200), (1500, (128, 256, 64), 3, 4, 64),
+                                         (800, (512, 1024, 512), 1, 6, 50)])
+def test_against_oracle_random(n, dims, L, T, B):
+    """Fresh random inputs at larger sizes: embeddings, loss and gradients vs the CPU oracle."""
+    rng = np.random.RandomState(n)
+    features = torch.tensor(rng.standard_normal((n, dims[0])), dtype=torch.float32)
+    nodes = np.stack([rng.choice(n, size=max(T, 8), replace=False) for _ in range(n)]).astype(np.int64)
+    w = (np.sort(rng.randint(1, 60, size=nodes.shape), axis=1)[:, ::-1] / 500.0).copy()
+    nbhds = (torch.from_numpy(w), torch.from_numpy(nodes))
+    params = oracle.make_params(L, dims, np.random.RandomState(n + 1))
+    batch = rng.randint(0, n, size=(B, 3)).astype(np.int64)
+    batch[1] = batch[0]  # a fully duplicated triple
+    o_loss, o_grads, (o_hq, _, o_hn) = oracle.train_batch_grads(params, features, batch, nbhds, T, L, 0.05)
+    model = _model(n, L, dims, T, nbhds, params)
+    feats = model.engine.features(features)
+    loss, emb, triples = model.engine.train_step(feats, torch.from_numpy(batch).cuda(), 0.05, True)
+    assert abs(float(loss) - float(o_loss)) < RTOL * abs(float(o_loss)) + 1e-9
+    assert rel(emb[triples[:, 0].long()], o_hq) < RTOL and rel(emb[triples[:, 2].long()], o_hn) < RTOL
+    for k, p in model.named_parameters():
+        assert rel(p.grad, o_grads[k]) < 5 * RTOL, k
+    # inference path == training forward
+    out = model.engine.embed(feats, torch.from_numpy(batch[:, 0]).cuda())
+    assert rel(out, o_hq) < RTOL
+    # without the compat factor the gradient is the plain autograd one: differs when duplicates exist
+    model.engine.train_step(feats, torch.from_numpy(batch).cuda(), 0.05, False)
+    assert rel(model.G2.weight.grad, o_grads["G2.weight"]) > 1e-3
+
+
+def test_state_dict_roundtrip_with_reference_keys(golden):
+    g = golden("model_small")
+    features, params, nbhds, n, L, T, dims = _inputs(g)
+    model = _model(n, L, dims, T, nbhds, params)
+    sd = model.state_dict()
+    assert list(sd) == list(params)
+    for k in params:
+        assert torch.equal(sd[k].cpu(), params[k])
