@@ -1,0 +1,365 @@
+#!/usr/bin/env python
+"""Benchmark of the PinSage hot path (BASELINE.json metric: train nodes/sec,
+sample+fwd+bwd; walk steps/sec).
+
+    python bench.py [--gpus N --steps K --warmup W] [--impl reference] [--workload cfg3|micro]
+
+Our arm (default): the drop-in trainer `pinsage_training.PinSage` on the synthetic
+1 M tracks / 200 k playlists / 40 M edges graph of BASELINE.json configs[2] (256-d
+features, 2 layers, T=50, batch 1024 per GPU, precomputed neighbourhoods as the reference
+does by default).  One step = sample a batch + PinSage.train_batch (shared-frontier
+forward, max-margin loss, backward, Adam).  `value` is timed with the batch sampled on the
+device (everything resident in HBM); `e2e` goes through the same public call with HOST
+batches: host sampling -> pinned buffer -> H2D -> step -> D2H of the loss, every step.
+Multi-GPU: one process per GPU (torchrun), data parallel, one NCCL allreduce of the flat
+gradient per step; weak scaling (batch 1024 per GPU).
+
+Reference arm (--impl reference): the CPU oracle port of the reference's train step
+(oracle/oracle.py, full-table clones and dense autograd included) on the box's host cores,
+same graph generator / config, bounded sample (small batch) per step.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+PKG = os.path.join(ROOT, "gcn-song-embeddings_b200")
+for p in (PKG, ROOT):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+METRIC = "pinsage_train_nodes_per_sec"
+UNIT = "nodes/s"
+
+WORKLOADS = {
+    # BASELINE.json configs[2]
+    "cfg3": dict(n_tracks=1_000_000, n_cols=200_000, n_edges=40_000_000, din=256, n_layers=2, T=50, batch=1024,
+                 n_pos=10_000_000, ref_batch=8),
+    # small stand-in for quick checks (not a bench line)
+    "micro": dict(n_tracks=20_000, n_cols=4_000, n_edges=400_000, din=256, n_layers=2, T=50, batch=256,
+                  n_pos=200_000, ref_batch=8),
+}
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(path):
+        with open(path) as f:
+            p = json.load(f)
+        return {"hbm_gbs": p["hbm_gbs"], "tflops": p.get("bf16_tflops_sustained", p["bf16_tflops"]), "source": "measured"}
+    return {"hbm_gbs": 6650.0, "tflops": 1400.0, "source": "fallback"}  # B200_PROFILING.md
+
+
+class ClockSampler:
+    """nvidia-smi clock / throttle-reason samples during the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.tmp = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(gpu_index)], stdout=self.tmp, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        self.tmp.flush(); self.tmp.seek(0)
+        sm, smax, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.tmp.read().splitlines():
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); smax.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, val in zip(names, f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        os.unlink(self.tmp.name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(smax) if smax else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def roofline_from_profile(summary, steps, peaks):
+    """Pick the kernel with the largest share of the step and report it against its bound."""
+    if not summary:
+        return None
+    total = sum(v["ms"] for v in summary.values())
+    tag, top = max(summary.items(), key=lambda kv: kv[1]["ms"])
+    per_launch_ms = top["ms"] / top["launches"]
+    is_gemm = tag.startswith("gemm")
+    if is_gemm:
+        achieved = top["flops"] / top["launches"] / (per_launch_ms * 1e-3) / 1e12
+        peak, unit, bound = peaks["tflops"], "TFLOP/s", "tensor"
+    else:
+        achieved = top["bytes"] / top["launches"] / (per_launch_ms * 1e-3) / 1e9
+        peak, unit, bound = peaks["hbm_gbs"], "GB/s", "hbm"
+    shares = {k: round(v["ms"] / total, 4) for k, v in sorted(summary.items(), key=lambda kv: -kv[1]["ms"])[:8]}
+    return {"kernel": tag, "bound": bound, "achieved": round(achieved, 2), "peak": peak, "unit": unit,
+            "frac": round(achieved / peak, 4), "traffic": None, "peak_source": peaks["source"],
+            "ms_per_launch": round(per_launch_ms, 4), "launches_per_step": top["launches"] / steps,
+            "share_of_kernel_time": round(top["ms"] / total, 4), "kernel_time_shares": shares,
+            "all": {k: {"ms_per_step": round(v["ms"] / steps, 4),
+                        "tflops": round(v["flops"] / (v["ms"] * 1e-3) / 1e12, 2) if v["ms"] > 0 else None,
+                        "gbs": round(v["bytes"] / (v["ms"] * 1e-3) / 1e9, 1) if v["ms"] > 0 else None}
+                    for k, v in summary.items()}}
+
+
+# ------------------------------------------------------------------------------------------
+# CPU baseline (oracle port of the reference's train step)
+# ------------------------------------------------------------------------------------------
+
+def cpu_train_baseline(features_cpu, nbhds_cpu, dims, n_layers, T, batches, warmup, margin=1e-5):
+    from oracle import oracle
+    params = oracle.make_params(n_layers, dims, np.random.RandomState(0))
+    tr = oracle.OracleTrainer(params, features_cpu, nbhds_cpu, T=T, n_layers=n_layers, margin=margin)
+    times = []
+    for i, b in enumerate(batches):
+        t0 = time.perf_counter()
+        tr.train_batch(b)
+        dt = time.perf_counter() - t0
+        if i >= warmup:
+            times.append(dt)
+    B = batches[0].shape[0]
+    return 3 * B / (sum(times) / len(times)), sum(times) / len(times)
+
+
+def needed_nbhds_cpu(indptr, indices, n_tracks, batches, T, n_layers, n_hops=500, alpha=0.85, Tp=100, seed=7):
+    """Neighbourhood rows for exactly the nodes the sample batches touch, from the oracle's
+    Philox walker (the reference arm has no GPU-side precompute to lean on)."""
+    from oracle import oracle
+    w = np.zeros((n_tracks, Tp), dtype=np.float64)
+    nodes = np.zeros((n_tracks, Tp), dtype=np.int64)
+    have = np.zeros(n_tracks, dtype=bool)
+    cur = np.unique(np.concatenate([b.reshape(-1) for b in batches]))
+    for _ in range(n_layers):
+        todo = cur[~have[cur]]
+        if todo.size:
+            trace = oracle.do_random_walks_philox(indptr, indices, todo, n_hops, alpha, seed)
+            ww, nn = oracle.topt_from_trace(trace, todo, Tp)
+            w[todo], nodes[todo], have[todo] = ww, nn, True
+        cur = np.unique(np.concatenate([nodes[cur, :T].reshape(-1), cur]))
+    return torch.from_numpy(w), torch.from_numpy(nodes)
+
+
+def run_reference(args, wl):
+    """--impl reference: the oracle port on the host cores."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    import ps_synth
+    torch.manual_seed(0)
+    t_setup = time.perf_counter()
+    indptr, indices, n_e = ps_synth.bipartite_csr(wl["n_tracks"], wl["n_cols"], wl["n_edges"], seed=1234, device="cpu")
+    feats = ps_synth.features(wl["n_tracks"], wl["din"], seed=1, device="cpu")
+    positives = ps_synth.cooccurrence_positives(indptr, indices, wl["n_tracks"], min(wl["n_pos"], 1_000_000), seed=2)
+    B = wl["ref_batch"]
+    rng = np.random.RandomState(3)
+    n_steps = args.warmup + args.steps
+    batches = []
+    for _ in range(n_steps):
+        pairs = positives[torch.from_numpy(rng.choice(positives.shape[0], B, replace=False))].numpy()
+        neg = rng.randint(0, wl["n_tracks"], size=(B, 1))
+        batches.append(np.concatenate([pairs, neg], 1).astype(np.int64))
+    nbhds = needed_nbhds_cpu(indptr.numpy(), indices.numpy(), wl["n_tracks"], batches, wl["T"], wl["n_layers"])
+    setup_s = time.perf_counter() - t_setup
+    value, s_per_step = cpu_train_baseline(feats, nbhds, (wl["din"], 512, 128), wl["n_layers"], wl["T"], batches, args.warmup)
+    cores = torch.get_num_threads()
+    line = {"impl": "reference", "metric": METRIC, "value": round(value, 3), "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(s_per_step * 1e3, 2),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(args.workload, wl, 1),
+            "cpu_baseline": {"value": round(value, 3), "unit": UNIT, "cores": cores, "kind": "port",
+                             "sample": f"{args.steps} steps of {B} triples (3*{B} nodes) on the full {wl['n_tracks']}-track graph, T={wl['T']}"},
+            "e2e": {"value": round(value, 3), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "setup_s": round(setup_s, 1)}
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+def workload_config(name, wl, n_gpus):
+    return {"workload": f"{name}: synthetic bipartite {wl['n_tracks']} tracks / {wl['n_cols']} playlists / {wl['n_edges']} edges, "
+                        f"{wl['din']}-d features, {wl['n_layers']} layers, T={wl['T']}, hidden 512, out 128, batch {wl['batch']}/GPU",
+            "sampling": "precomputed neighbourhoods (n_hops=500, alpha=0.85, T_precomp=100), easy negatives",
+            "global_batch": wl["batch"] * n_gpus, "parallelism": f"dp{n_gpus}",
+            "l2_policy": "inputs larger than L2 (features 1.0 GB, transformed rows up to 2 GB per step vs 126 MB L2)"}
+
+
+# ------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------
+
+def run_ours(args, wl):
+    import ps_dist
+    import ps_native
+    import ps_synth
+    import pinsage_model as psm
+    import pinsage_training as pst
+
+    rank, world, local = ps_dist.init_from_env()
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm")
+    dev = torch.device("cuda", local)
+    peaks = load_peaks()
+    torch.manual_seed(1000 + rank)
+    N, C, din, T, B, L = wl["n_tracks"], wl["n_cols"], wl["din"], wl["T"], wl["batch"], wl["n_layers"]
+
+    # ---- setup (untimed): graph, features, positives resident in HBM ----
+    g = ps_synth.make_graph(N, C, wl["n_edges"], seed=1234, device="cuda")
+    gh = g.device()
+    feats = ps_synth.features(N, din, seed=1, device="cuda")
+    positives = ps_synth.cooccurrence_positives(gh.indptr, gh.indices, N, wl["n_pos"], seed=2)
+
+    # ---- walker microbench (BASELINE.json "walk steps/sec"): all N sources x 500 hops, T=100 ----
+    all_src = torch.arange(N, device="cuda")
+    ps_native.walk_topt(gh, all_src[: max(1, N // 16)], 500, 0.85, 100, seed=1, want_i64=False, want_i32=True)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    ps_native.walk_topt(gh, all_src, 500, 0.85, 100, seed=2, want_i64=False, want_i32=True)
+    e1.record(); torch.cuda.synchronize()
+    walk_ms = e0.elapsed_time(e1)
+    walk_steps_per_s = N * 500 / (walk_ms * 1e-3)
+
+    # ---- the trainer, through the public drop-in API ----
+    cwd = os.getcwd()
+    tmp = tempfile.mkdtemp(prefix="psbench_")
+    os.chdir(tmp)
+    os.makedirs("runs", exist_ok=True)
+    try:
+        trainer = pst.PinSage(g, N, feats, positives, log=False, load_save=False)
+    finally:
+        os.chdir(cwd)
+    trainer.T = T; trainer.model.T = T
+    trainer.batch_size = B
+    ps_dist.attach(trainer, rank, world)
+    nbhds_cpu = trainer.nbhds
+
+    def device_step():
+        batch, _ = pst.sample_batch(trainer.all_ids, positives, B, trainer.nbhds, hard_negatives=False)
+        return trainer.train_batch(batch)
+
+    for _ in range(args.warmup):
+        device_step()
+    torch.cuda.synchronize(); ps_dist.barrier()
+
+    # ---- timed region: K steps, device-resident inputs ----
+    sampler = ClockSampler(local) if rank == 0 else None
+    ps_native.profiler = ps_native.Profiler()
+    launches0 = ps_native.launch_count
+    t0 = torch.cuda.Event(enable_timing=True); t1 = torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize(); ps_dist.barrier()
+    w0 = time.perf_counter()
+    t0.record()
+    for _ in range(args.steps):
+        loss, _, _ = device_step()
+    t1.record()
+    torch.cuda.synchronize(); ps_dist.barrier()
+    wall = time.perf_counter() - w0
+    dev_ms = t0.elapsed_time(t1)
+    launches = ps_native.launch_count - launches0
+    clocks = sampler.stop() if sampler else None
+    prof = ps_native.profiler.summary(); ps_native.profiler = None
+    step_ms = ps_dist.max_over_ranks(max(dev_ms, 0.0) / args.steps)
+    wall_ms = ps_dist.max_over_ranks(wall * 1e3 / args.steps)
+    # device events bracket the region; the wall clock is reported beside it (host-side frontier construction
+    # synchronises, so the two agree)
+    value = 3 * B * world / (step_ms * 1e-3)
+    final_loss = float(loss)
+
+    # ---- e2e: the same public call with HOST batches (pinned -> H2D -> step -> D2H of the loss) ----
+    pos_cpu = positives.cpu()
+    ids_cpu = torch.arange(N)
+    pinned = torch.empty((B, 3), dtype=torch.int64).pin_memory()
+
+    def e2e_step():
+        batch, _ = pst.sample_batch(ids_cpu, pos_cpu, B, nbhds_cpu, hard_negatives=False)
+        pinned.copy_(batch)
+        out = trainer.train_batch(pinned)
+        return float(out[0])  # D2H read of the step's result
+
+    for _ in range(args.warmup):
+        e2e_step()
+    torch.cuda.synchronize(); ps_dist.barrier()
+    w0 = time.perf_counter()
+    for _ in range(args.steps):
+        e2e_step()
+    torch.cuda.synchronize(); ps_dist.barrier()
+    e2e_ms = ps_dist.max_over_ranks((time.perf_counter() - w0) * 1e3 / args.steps)
+    e2e_value = 3 * B * world / (e2e_ms * 1e-3)
+
+    if args.torch_profile and rank == 0:  # optional: where the non-kernel time of a step goes (not a bench number)
+        from torch.profiler import ProfilerActivity, profile
+        with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA]) as tp:
+            for _ in range(3):
+                device_step()
+            torch.cuda.synchronize()
+        with open(args.torch_profile, "w") as f:
+            f.write(tp.key_averages().table(sort_by="cuda_time_total", row_limit=60, max_name_column_width=70))
+
+    line = {"metric": METRIC, "value": round(value, 1), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": round(step_ms, 3), "wall_ms_per_step": round(wall_ms, 3),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic", "config": workload_config(args.workload, wl, world),
+            "e2e": {"value": round(e2e_value, 1), "unit": UNIT, "ms_per_step": round(e2e_ms, 3),
+                    "h2d_bytes_per_step": B * 3 * 8, "d2h_bytes_per_step": 4},
+            "gpu_launches": launches, "clocks": clocks,
+            "walk": {"metric": "walk_steps_per_sec", "value": round(walk_steps_per_s, 1), "unit": "steps/s",
+                     "sources": N, "n_hops": 500, "alpha": 0.85, "T": 100, "ms": round(walk_ms, 3),
+                     "algorithmic_gbs": round(walk_steps_per_s * 28 / 1e9, 2),
+                     "frac_of_hbm": round(walk_steps_per_s * 28 / 1e9 / peaks["hbm_gbs"], 4)},
+            "final_loss": final_loss}
+    if rank == 0:
+        line["roofline"] = roofline_from_profile(prof, args.steps, peaks)
+        if world == 1 and not args.no_cpu_baseline:
+            Bc = wl["ref_batch"]
+            cpu_batches = [pst.sample_batch(ids_cpu, pos_cpu, Bc, nbhds_cpu, hard_negatives=False)[0].numpy() for _ in range(3)]
+            cv, cs = cpu_train_baseline(feats.cpu(), nbhds_cpu, (din, 512, 128), L, T, cpu_batches, warmup=1)
+            line["cpu_baseline"] = {"value": round(cv, 3), "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+                                    "sample": f"2 timed steps (1 warm-up) of {Bc} triples (3*{Bc} nodes) on the same {N}-track graph, T={T}; {cs:.2f} s/step"}
+        print(json.dumps(line), flush=True)
+    ps_dist.barrier()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="cfg3", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--torch-profile", default=None, help="write a torch.profiler kernel table of 3 extra steps here")
+    args = ap.parse_args()
+    wl = WORKLOADS[args.workload]
+    if args.impl == "reference":
+        return run_reference(args, wl)
+    if args.warmup < 3:
+        print("note: fewer than 3 warm-up steps requested; the contract asks for W >= 3", file=sys.stderr)
+    return run_ours(args, wl)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -22,7 +22,7 @@ struct ps_graph {
 
 namespace {
 
-constexpr int kWarpsPerCta = 8;
+constexpr int kMaxWarpsPerCta = 8;  // fewer when the per-warp trace (8 B x pow2(n_hops)) is large
 constexpr uint32_t kPad = 0xFFFFFFFFu;
 
 struct Philox {
@@ -72,7 +72,7 @@ __device__ __forceinline__ void warp_bitonic_sort(uint32_t* a, int P, int lane) 
 
 // kFromTrace: read the steps from a caller-supplied trace instead of walking (parity hook)
 template <bool kFromTrace>
-__global__ void __launch_bounds__(kWarpsPerCta * 32)
+__global__ void __launch_bounds__(kMaxWarpsPerCta * 32)
 walk_topt_kernel(const int64_t* __restrict__ indptr, const int32_t* __restrict__ indices,
                  const int64_t* __restrict__ sources, const int64_t* __restrict__ in_trace,
                  int64_t n, int n_hops, int P, uint64_t restart_thr, int fixed_len, int T,
@@ -86,8 +86,9 @@ walk_topt_kernel(const int64_t* __restrict__ indptr, const int32_t* __restrict__
     uint32_t* ids = smem + static_cast<size_t>(warp) * 2 * P;  // trace, then sorted ids
     uint32_t* keys = ids + P;                                 // (count << 16) | (0xFFFF - head position)
 
-    for (int64_t s = static_cast<int64_t>(blockIdx.x) * kWarpsPerCta + warp; s < n;
-         s += static_cast<int64_t>(gridDim.x) * kWarpsPerCta) {
+    const int warps_per_cta = blockDim.x >> 5;
+    for (int64_t s = static_cast<int64_t>(blockIdx.x) * warps_per_cta + warp; s < n;
+         s += static_cast<int64_t>(gridDim.x) * warps_per_cta) {
         const uint32_t src = static_cast<uint32_t>(sources[s]);
 
         if (kFromTrace) {
@@ -181,26 +182,29 @@ template <bool kFromTrace>
 int launch_walk(const int64_t* indptr, const int32_t* indices, const int64_t* sources, const int64_t* trace,
                 int64_t n, int n_hops, double alpha, int fixed_len, int T, uint64_t seed,
                 int64_t* on64, double* ow64, int32_t* on32, float* ow32, int32_t* otrace, cudaStream_t stream) {
-    PS_REQUIRE(n >= 0 && n_hops > 0 && n_hops <= 32768, "n_hops must be in [1, 32768] (got %d)", n_hops);
+    PS_REQUIRE(n >= 0 && n_hops > 0 && n_hops <= 16384, "n_hops must be in [1, 16384] (got %d)", n_hops);
     PS_REQUIRE(T > 0, "T must be positive");
     PS_REQUIRE(alpha >= 0.0 && alpha <= 1.0, "alpha must be in [0, 1]");
     if (n == 0) return PS_OK;
     const int P = next_pow2(n_hops);
-    const size_t smem = static_cast<size_t>(kWarpsPerCta) * 2 * P * sizeof(uint32_t);
-    PS_REQUIRE(smem <= 200 * 1024, "n_hops too large for the shared-memory trace");
+    const size_t per_warp = 2 * static_cast<size_t>(P) * sizeof(uint32_t);
+    int warps = static_cast<int>((200 * 1024) / per_warp);
+    if (warps > kMaxWarpsPerCta) warps = kMaxWarpsPerCta;
+    PS_REQUIRE(warps >= 1, "n_hops=%d too large for the shared-memory trace (max 16384)", n_hops);
+    const size_t smem = static_cast<size_t>(warps) * per_warp;
     auto kern = walk_topt_kernel<kFromTrace>;
     if (smem > 48 * 1024)
         PS_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
     int dev = 0, sms = 148, occ = 1;
     PS_CUDA_CHECK(cudaGetDevice(&dev));
     PS_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    PS_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kWarpsPerCta * 32, smem));
+    PS_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, warps * 32, smem));
     if (occ < 1) occ = 1;
-    int64_t blocks = ps_ceil_div(n, kWarpsPerCta);
+    int64_t blocks = ps_ceil_div(n, warps);
     const int64_t resident = static_cast<int64_t>(sms) * occ;  // persistent: grid-stride over sources
     if (blocks > resident * 4) blocks = resident * 4;
     const uint64_t thr = static_cast<uint64_t>(alpha * 4294967296.0);
-    kern<<<static_cast<unsigned>(blocks), kWarpsPerCta * 32, smem, stream>>>(
+    kern<<<static_cast<unsigned>(blocks), warps * 32, smem, stream>>>(
         indptr, indices, sources, trace, n, n_hops, P, thr, fixed_len, T,
         static_cast<uint32_t>(seed & 0xFFFFFFFFull), static_cast<uint32_t>(seed >> 32), on64, ow64, on32, ow32, otrace);
     PS_LAUNCH_CHECK();

@@ -1,0 +1,77 @@
+"""Data parallelism for the PinSage trainer: one process per GPU, graph / features /
+neighbourhood table replicated in each GPU's HBM, each rank draws its own batches, and the
+only exchange per step is one allreduce of the flat fp32 gradient buffer (~1.6-2.3 MB)
+over NCCL (NVLink 5 / NVSwitch).  Full-graph inference shards by node range with no
+communication.  The reference is single-process; this is the one
+parallelism strategy the engine adds (section 8e).
+
+The helpers are backend-agnostic (`gloo` on CPU in the tests, `nccl` on GPUs)."""
+from __future__ import annotations
+
+import os
+
+import torch
+import torch.distributed as dist
+
+
+def init_from_env(backend=None):
+    """Initialise torch.distributed from torchrun's env (RANK / WORLD_SIZE / LOCAL_RANK /
+    MASTER_*).  Returns (rank, world_size, local_rank); a no-op single-process world when
+    WORLD_SIZE is unset or 1."""
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if torch.cuda.is_available():
+        torch.cuda.set_device(local)
+    if world > 1 and not dist.is_initialized():
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("MASTER_PORT", "29500")
+        dist.init_process_group(backend or ("nccl" if torch.cuda.is_available() else "gloo"),
+                                rank=rank, world_size=world)
+    return rank, world, local
+
+
+def allreduce_mean_(flat: torch.Tensor, world_size: int):
+    """In-place mean of a flat gradient buffer over all ranks."""
+    if world_size > 1:
+        dist.all_reduce(flat, op=dist.ReduceOp.SUM)
+        flat.div_(world_size)
+    return flat
+
+
+def broadcast_parameters(model, src=0):
+    """Make every rank start from rank `src`'s parameters."""
+    if dist.is_initialized() and dist.get_world_size() > 1:
+        for p in model.parameters():
+            dist.broadcast(p.data, src=src)
+
+
+def attach(trainer, rank: int, world_size: int):
+    """Turn a PinSage trainer into one data-parallel replica: parameters broadcast from
+    rank 0, gradient mean-allreduce before every optimiser step."""
+    trainer.rank, trainer.world_size = rank, world_size
+    if world_size > 1:
+        broadcast_parameters(trainer.model)
+        engine = trainer.model.engine
+        trainer._grad_sync = lambda: allreduce_mean_(engine.flat_grad, world_size)
+    return trainer
+
+
+def shard_range(n: int, rank: int, world_size: int):
+    """Contiguous node range [lo, hi) of rank `rank` (full-graph inference shards)."""
+    per = -(-n // world_size)
+    lo = min(n, rank * per)
+    return lo, min(n, lo + per)
+
+
+def max_over_ranks(value: float, device=None) -> float:
+    if not (dist.is_initialized() and dist.get_world_size() > 1):
+        return value
+    t = torch.tensor([value], dtype=torch.float64, device=device or ("cuda" if dist.get_backend() == "nccl" else "cpu"))
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t[0])
+
+
+def barrier():
+    if dist.is_initialized() and dist.get_world_size() > 1:
+        dist.barrier()

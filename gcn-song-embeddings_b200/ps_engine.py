@@ -161,14 +161,14 @@ class Engine:
             conv = m.conv_layers[l]
             din = in_dims[l]
             z = torch.empty((lp.nz, dh), dtype=torch.float32, device="cuda")
-            nat.gemm(h_prev, conv.Q.weight, z, lp.nz, dh, din, p_rows=lp.zrows, bias=conv.Q.bias, act=1)
+            nat.gemm(h_prev, conv.Q.weight, z, lp.nz, dh, din, p_rows=lp.zrows, bias=conv.Q.bias, act=1, tag=f"gemm_q_fwd_l{l}")
             cat = torch.empty((lp.n, din + dh), dtype=torch.float32, device="cuda")
             inv_wsum = torch.empty((lp.n,), dtype=torch.float32, device="cuda")
-            nat.aggregate_fwd(h_prev, lp.self_rows, din, z, lp.nbz, lp.w, dh, cat, inv_wsum)
+            nat.aggregate_fwd(h_prev, lp.self_rows, din, z, lp.nbz, lp.w, dh, cat, inv_wsum, tag=f"aggregate_fwd_l{l}")
             h = torch.empty((lp.n, do), dtype=torch.float32, device="cuda")
             norm = torch.empty((lp.n,), dtype=torch.float32, device="cuda")
             if do <= 128:
-                nat.gemm(cat, conv.W.weight, h, lp.n, do, din + dh, bias=conv.W.bias, act=1, l2norm=True, norm_out=norm)
+                nat.gemm(cat, conv.W.weight, h, lp.n, do, din + dh, bias=conv.W.bias, act=1, l2norm=True, norm_out=norm, tag=f"gemm_w_fwd_l{l}")
             else:
                 nat.gemm(cat, conv.W.weight, h, lp.n, do, din + dh, bias=conv.W.bias, act=1)
                 nat.l2norm_rows(h, norm)
@@ -214,29 +214,38 @@ class Engine:
             d_pre = torch.empty((lp.n, do), dtype=torch.float32, device="cuda")
             nat.norm_leaky_bwd(h, norm, d_h, d_pre)
             nat.gemm(d_pre, cat, grads[pre + "W.weight"], do, din + dh, lp.n, p_kmajor=False, q_kmajor=False,
-                     accumulate=True, splits=_splits_for(do, din + dh, lp.n))
+                     accumulate=True, splits=_splits_for(do, din + dh, lp.n), tag=f"gemm_w_wgrad_l{l}")
             nat.colsum(d_pre, grads[pre + "W.bias"])
             d_cat = torch.empty((lp.n, din + dh), dtype=torch.float32, device="cuda")
-            nat.gemm(d_pre, conv.W.weight, d_cat, lp.n, din + dh, do, q_kmajor=False)
-            nat.aggregate_bwd(d_cat, din, dh, lp.seg_off, lp.pair_q, lp.w, inv_wsum, lp.w.shape[1], z)  # z := dZ_pre
+            nat.gemm(d_pre, conv.W.weight, d_cat, lp.n, din + dh, do, q_kmajor=False, tag=f"gemm_w_dgrad_l{l}")
+            nat.aggregate_bwd(d_cat, din, dh, lp.seg_off, lp.pair_q, lp.w, inv_wsum, lp.w.shape[1], z, tag=f"aggregate_bwd_l{l}")  # z := dZ_pre
             nat.gemm(z, h_in, grads[pre + "Q.weight"], dh, din, lp.nz, p_kmajor=False, q_kmajor=False,
-                     q_rows=lp.zrows, accumulate=True, splits=_splits_for(dh, din, lp.nz))
+                     q_rows=lp.zrows, accumulate=True, splits=_splits_for(dh, din, lp.nz), tag=f"gemm_q_wgrad_l{l}")
             nat.colsum(z, grads[pre + "Q.bias"])
             if l > 0:
                 d_h = torch.empty((lp.nz, din), dtype=torch.float32, device="cuda")
-                nat.gemm(z, conv.Q.weight, d_h, lp.nz, din, dh, q_kmajor=False)
+                nat.gemm(z, conv.Q.weight, d_h, lp.nz, din, dh, q_kmajor=False, tag=f"gemm_q_dgrad_l{l}")
                 nat.scatter_add_rows(d_cat, lp.self_rows, d_h, din)
         return grads
 
     def zero_grads(self):
-        """Dict name -> zeroed gradient tensor; reuses (and zeroes) the parameters' .grad."""
-        grads = {}
-        for name, p in self.model.named_parameters():
-            if p.grad is None:
-                p.grad = torch.zeros_like(p)
-            else:
-                p.grad.zero_()
-            grads[name] = p.grad
+        """Dict name -> zeroed gradient tensor.  All gradients are views into ONE flat fp32
+        buffer (self.flat_grad) installed as the parameters' .grad, so the data-parallel
+        exchange is a single allreduce and zeroing a single memset."""
+        params = list(self.model.named_parameters())
+        total = sum(p.numel() for _, p in params)
+        flat = getattr(self, "flat_grad", None)
+        if flat is None or flat.numel() != total or flat.device != params[0][1].device:
+            flat = self.flat_grad = torch.zeros(total, dtype=torch.float32, device=params[0][1].device)
+        else:
+            flat.zero_()
+        grads, off = {}, 0
+        for name, p in params:
+            view = flat[off: off + p.numel()].view_as(p)
+            if p.grad is None or p.grad.data_ptr() != view.data_ptr():
+                p.grad = view
+            grads[name] = view
+            off += p.numel()
         return grads
 
     # ---- fused training step -----------------------------------------------------------
@@ -282,7 +291,7 @@ class PinSageFunction(torch.autograd.Function):
     def forward(ctx, engine: Engine, feats, nodeset, reference_compat, *params):
         top, inv = torch.unique(nodeset, return_inverse=True)
         m = engine.model
-        need = any(p.requires_grad for p in params) and torch.is_grad_enabled()
+        need = any(ctx.needs_input_grad[4:])  # (grad mode is off inside Function.forward)
         plan = build_plan(top, m.n_layers, m.T, NeighborTable.of(m.nbhds), need_backward=need)
         out, saved = engine.forward(feats, plan, keep=need)
         ctx.engine, ctx.saved, ctx.inv, ctx.n_top, ctx.compat = engine, saved, inv, top.numel(), reference_compat

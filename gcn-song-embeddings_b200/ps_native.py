@@ -108,6 +108,47 @@ def _p(t, dtype=None):
 launch_count = 0  # kernel-launching ABI calls made so far (bench.py reports the per-step delta)
 
 
+class Profiler:
+    """CUDA-event timing of individual ABI calls on the launching stream (bench.py's
+    roofline leg).  Recording an event does not synchronise; summary() does."""
+
+    def __init__(self):
+        self.records = []
+
+    def summary(self):
+        torch.cuda.synchronize()
+        out = {}
+        for tag, e0, e1, flops, nbytes in self.records:
+            d = out.setdefault(tag, {"ms": 0.0, "launches": 0, "flops": 0.0, "bytes": 0.0})
+            d["ms"] += e0.elapsed_time(e1)
+            d["launches"] += 1
+            d["flops"] += flops
+            d["bytes"] += nbytes
+        return out
+
+
+profiler = None  # set to a Profiler() to time every ABI call
+
+
+class _Timed:
+    __slots__ = ("tag", "flops", "nbytes", "e0")
+
+    def __init__(self, tag, flops=0.0, nbytes=0.0):
+        self.tag, self.flops, self.nbytes = tag, flops, nbytes
+
+    def __enter__(self):
+        if profiler is not None:
+            self.e0 = torch.cuda.Event(enable_timing=True)
+            self.e0.record()
+
+    def __exit__(self, *exc):
+        if profiler is not None:
+            e1 = torch.cuda.Event(enable_timing=True)
+            e1.record()
+            profiler.records.append((self.tag, self.e0, e1, self.flops, self.nbytes))
+        return False
+
+
 def _stream():
     global launch_count
     launch_count += 1
@@ -182,23 +223,41 @@ def trace_topt(trace: torch.Tensor, sources: torch.Tensor, T: int):
 # ------------------------------------------------------------------------------------
 
 def gemm(P, Q, C, M, N, K, *, p_kmajor=True, q_kmajor=True, p_rows=None, q_rows=None, bias=None,
-         act=0, l2norm=False, norm_out=None, accumulate=False, splits=1):
+         act=0, l2norm=False, norm_out=None, accumulate=False, splits=1, tag="gemm"):
     """C[i,j] (+)= act(sum_r P(i,r) Q(j,r) + bias[j]); see ps_gemm in the header."""
+    with _Timed(tag, 2.0 * M * N * K, 4.0 * (M * K + N * K + M * N)):
+        _gemm(P, Q, C, M, N, K, p_kmajor, q_kmajor, p_rows, q_rows, bias, act, l2norm, norm_out, accumulate, splits)
+
+
+def _gemm(P, Q, C, M, N, K, p_kmajor, q_kmajor, p_rows, q_rows, bias, act, l2norm, norm_out, accumulate, splits):
     check(lib().ps_gemm(_p(P, torch.float32), _ld(P), int(p_kmajor), _p(p_rows, torch.int32),
                         _p(Q, torch.float32), _ld(Q), int(q_kmajor), _p(q_rows, torch.int32),
                         _p(C, torch.float32), _ld(C), int(M), int(N), int(K), _p(bias, torch.float32),
                         int(act), int(l2norm), _p(norm_out, torch.float32), int(accumulate), int(splits), _stream()))
 
 
-def aggregate_fwd(hin, self_rows, din, z, nbz, nbw, dh, cat, inv_wsum):
+def aggregate_fwd(hin, self_rows, din, z, nbz, nbw, dh, cat, inv_wsum, tag="aggregate_fwd"):
     n, T = nbz.shape
+    # algorithmic bytes: T gathered dh-wide rows + the self row, indices + weights, the [din+dh] output row
+    with _Timed(tag, 2.0 * n * T * dh, float(n) * (T * dh * 4 + din * 4 + T * 8 + 4 + (din + dh) * 4 + 4)):
+        _aggregate_fwd(hin, self_rows, din, z, nbz, nbw, dh, cat, inv_wsum, n, T)
+
+
+def _aggregate_fwd(hin, self_rows, din, z, nbz, nbw, dh, cat, inv_wsum, n, T):
     check(lib().ps_aggregate_fwd(_p(hin, torch.float32), _ld(hin), _p(self_rows, torch.int32), int(din),
                                  _p(z, torch.float32), _ld(z), _p(nbz, torch.int32), _p(nbw, torch.float32),
                                  int(T), int(dh), int(n), _p(cat, torch.float32), _ld(cat),
                                  _p(inv_wsum, torch.float32), _stream()))
 
 
-def aggregate_bwd(dcat, col_off, dh, seg_off, pair_q, nbw, inv_wsum, T, z):
+def aggregate_bwd(dcat, col_off, dh, seg_off, pair_q, nbw, inv_wsum, T, z, tag="aggregate_bwd"):
+    pairs, nz = pair_q.numel(), z.shape[0]
+    # algorithmic bytes: one dh-wide dcat row per (target, slot) pair + pair index/weight/inv_wsum, Z read + written
+    with _Timed(tag, 2.0 * pairs * dh, float(pairs) * (dh * 4 + 12) + float(nz) * (2 * dh * 4 + 8)):
+        _aggregate_bwd(dcat, col_off, dh, seg_off, pair_q, nbw, inv_wsum, T, z)
+
+
+def _aggregate_bwd(dcat, col_off, dh, seg_off, pair_q, nbw, inv_wsum, T, z):
     check(lib().ps_aggregate_bwd(_p(dcat, torch.float32), _ld(dcat), int(col_off), int(dh),
                                  _p(seg_off, torch.int32), _p(pair_q, torch.int32), _p(nbw, torch.float32),
                                  _p(inv_wsum, torch.float32), int(T), _p(z, torch.float32), _ld(z),

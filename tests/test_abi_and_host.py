@@ -1,0 +1,163 @@
+"""CPU-side checks: the C-ABI library loads and exports every symbol the header declares
+(no compute calls without a GPU), and the host logic (CSR graph, frontier plans, batch
+sampling, synthetic data) behaves like the reference's."""
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import oracle
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    import ps_native
+    header = open(os.path.join(ROOT, "include", "pinsage_b200.h")).read()
+    declared = set(re.findall(r"\b(ps_[a-z0-9_]+)\s*\(", header))
+    declared -= {"ps_graph_t", "ps_stream_t"}
+    assert len(declared) >= 18
+    lib = ps_native.load_library()  # dlopen only; raises AttributeError on a missing symbol
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert declared == set(ps_native.EXPORTED_SYMBOLS)
+    assert lib.ps_version() == 1
+
+
+def test_no_cpu_fallback_without_device():
+    import ps_native
+    if torch.cuda.is_available():
+        pytest.skip("device present")
+    with pytest.raises(ps_native.NativeError, match="no CPU fallback"):
+        ps_native._ensure_device()
+    import pinsage_model as psm
+    with pytest.raises(ps_native.NativeError):
+        psm.PinSageModel(None, 10, 2, (8, 8, 4), 500, 0.85, 3, (torch.zeros(10, 3, dtype=torch.float64), torch.zeros(10, 3, dtype=torch.int64)))
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "gcn-song-embeddings_b200")
+    for fn in os.listdir(pkg):
+        if fn.endswith(".py"):
+            src = open(os.path.join(pkg, fn)).read()
+            assert "oracle" not in src.replace("# oracle", ""), fn
+
+
+def test_psgraph_matches_dgl_semantics(golden):
+    from ps_graph import PSGraph
+    rng = np.random.RandomState(0)
+    nt, nc = 30, 8
+    t = rng.randint(0, nt, 100); c = rng.randint(0, nc, 100) + nt
+    src, dst = np.r_[t, c], np.r_[c, t]
+    g = PSGraph.from_edges(src, dst, nt, nc, nbhds_path="x.pt")
+    assert g.number_of_nodes() == len(g) == nt + nc and g.nbhds_path == "x.pt"
+    for v in (0, 5, nt + 2):
+        want = dst[src == v]  # insertion order per source, multi-edges kept (DGL)
+        assert np.array_equal(g.successors(v).numpy(), want)
+    assert int(g.out_degrees().sum()) == 200 and torch.equal(g.in_degrees(), g.out_degrees())
+    s2, d2 = g.edges()
+    assert sorted(zip(s2.tolist(), d2.tolist())) == sorted(zip(src.tolist(), dst.tolist()))
+    with pytest.raises(IndexError):
+        PSGraph.from_edges([0, 99], [1, 2], nt, nc)
+
+
+@pytest.mark.parametrize("tag,L,T", [("L2T3", 2, 3), ("L3T5", 3, 5), ("L2T10", 2, 10)])
+def test_build_plan_matches_reference_frontier(golden, tag, L, T):
+    """Engine plans (CPU tensors) reproduce relevant_nodes_per_layer_precomp on the distinct
+    batch nodes, and the backward transpose lists every (target, slot) pair exactly once."""
+    import ps_engine
+    g = golden("frontier")
+    tab = ps_engine.NeighborTable(torch.from_numpy(g["w"]), torch.from_numpy(g["nodes"]), device="cpu")
+    top = torch.unique(torch.from_numpy(g[f"{tag}_nodeset"]))
+    plan = ps_engine.build_plan(top, L, T, tab, need_backward=True)
+    S = oracle.relevant_nodes_per_layer_precomp(top.numpy(), L, T, (g["w"], g["nodes"]))
+    # lower layers of the reference frontier are those of the ORIGINAL (duplicated) nodeset too
+    S_dup = [(g[f"{tag}_ns{l}"], g[f"{tag}_w{l}"], g[f"{tag}_nb{l}"]) for l in range(L)]
+    for l in range(L - 1):
+        assert np.array_equal(S[l][0], S_dup[l][0])
+    for l, (ns, w, nb) in enumerate(S):
+        lp = plan.layers[l]
+        if l == 0:
+            ids = lp.zrows.long()[lp.nbz.long()]
+            assert np.array_equal(lp.self_rows.numpy(), ns)
+        else:
+            prev = torch.from_numpy(S[l - 1][0])
+            ids = prev[lp.nbz.long()]
+            assert np.array_equal(prev[lp.self_rows.long()].numpy(), ns)
+        assert np.array_equal(ids.numpy(), nb)
+        assert np.array_equal(lp.w.numpy(), w.astype(np.float32))
+        flat = lp.nbz.reshape(-1)
+        assert sorted(lp.pair_q.tolist()) == list(range(flat.numel()))
+        for u in range(lp.nz):
+            seg = lp.pair_q[lp.seg_off[u]:lp.seg_off[u + 1]].long()
+            assert bool((flat[seg] == u).all())
+    with pytest.raises(IndexError):
+        ps_engine.build_plan(torch.tensor([10 ** 6]), L, T, tab, False)
+    with pytest.raises(ValueError):
+        ps_engine.build_plan(top, L, 999, tab, False)
+
+
+@pytest.mark.parametrize("n,P,B", [(500, 2000, 64), (200_000, 3_000_000, 512)])
+def test_batch_sampling_properties(n, P, B):
+    """Same guarantees as the reference's sample_batch with easy negatives: distinct rows of
+    `positives`, distinct negatives outside the batch (pinsage_training.py:53-77)."""
+    import pinsage_training as pst
+    torch.manual_seed(0)
+    positives = torch.unique(torch.randint(0, n, (P, 2)), dim=0)
+    all_ids = torch.arange(n)
+    batch, nodeset = pst.sample_batch(all_ids, positives, B, None, hard_negatives=False)
+    assert batch.shape == (B, 3) and batch.dtype == torch.int64
+    oracle.check_batch_properties(batch.numpy(), positives.numpy(), n)
+    assert len({tuple(r) for r in batch[:, :2].tolist()}) == B  # pairs drawn without repetition
+    assert torch.equal(nodeset, batch.flatten().unique())
+    # hard negatives: rank window and the reference's row quirk
+    nb = torch.randint(0, n, (n, 100))
+    hb, _ = pst.sample_batch(all_ids, positives, B, (None, nb), hard_negatives=True, hn_min=10, hn_max=20)
+    assert all(int(hb[i, 2]) in nb[i, 10:20].tolist() for i in range(B))  # rows 0..B-1, pinsage_training.py:84
+    fixed, _ = pst.sample_hard_negatives(all_ids, hb[:, :2], (None, nb), 10, 20, reference_compat=False)
+    assert all(int(fixed[i, 2]) in nb[int(fixed[i, 0]), 10:20].tolist() for i in range(B))
+
+
+def test_distinct_randint_is_uniform_without_replacement():
+    import pinsage_training as pst
+    torch.manual_seed(1)
+    hits = torch.zeros(100_000)
+    for _ in range(50):
+        s = pst._distinct_randint(100_000, 2000, "cpu")
+        assert s.numel() == 2000 and s.unique().numel() == 2000
+        hits[s] += 1
+    assert abs(float(hits.mean()) - 1.0) < 1e-6 and float(hits.max()) <= 8
+
+
+def test_synthetic_graph_properties():
+    import ps_synth
+    nt, nc = 5000, 800
+    indptr, indices, e = ps_synth.bipartite_csr(nt, nc, 60_000, seed=9)
+    deg = indptr[1:] - indptr[:-1]
+    assert int(deg.min()) >= 1 and indices.numel() == 2 * e == int(indptr[-1])
+    t_side = indices[: int(indptr[nt])]; c_side = indices[int(indptr[nt]):]
+    assert int(t_side.min()) >= nt and int(c_side.max()) < nt  # bipartite
+    src = torch.repeat_interleave(torch.arange(nt + nc), deg)
+    fwd = set(zip(src.tolist(), indices.tolist()))
+    assert all((b, a) in fwd for a, b in list(fwd)[:2000])  # both directions listed
+    assert len(fwd) == 2 * e  # no duplicate memberships
+    pos = ps_synth.cooccurrence_positives(indptr, indices, nt, 500)
+    for a, b in pos[:50].tolist():
+        ca = set(indices[indptr[a]:indptr[a + 1]].tolist()); cb = set(indices[indptr[b]:indptr[b + 1]].tolist())
+        assert a != b and ca & cb
+    f = ps_synth.features(nt, 16)
+    assert torch.allclose(f.mean(0), torch.zeros(16), atol=1e-5) and torch.allclose(f.std(0), torch.ones(16), atol=1e-4)
+
+
+def test_metrics_match_oracle(golden):
+    g = golden("metrics_knn")
+    import ps_eval
+    knn = torch.from_numpy(g["rnd_knn"]); pos = torch.from_numpy(g["rnd_pos"])
+    for K, hr, m in zip(g["rnd_K"], g["rnd_hr"], g["rnd_mrr"]):
+        assert ps_eval.hit_rate(knn, pos, int(K)) == pytest.approx(hr, abs=1e-12)
+        assert ps_eval.mrr(knn, pos, int(K)) == pytest.approx(m, abs=1e-12)
+    for K, hr, m in zip(g["toy_K"], g["toy_hr"], g["toy_mrr"]):
+        assert ps_eval.hit_rate(torch.from_numpy(g["toy_knn"]), torch.from_numpy(g["toy_pos"]), int(K)) == pytest.approx(hr)
+        assert ps_eval.mrr(torch.from_numpy(g["toy_knn"]), torch.from_numpy(g["toy_pos"]), int(K)) == pytest.approx(m)

@@ -1,0 +1,80 @@
+"""world_size-2 `gloo` tests (CPU) of the data-parallel host logic in ps_dist."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+
+def _free_port():
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); p = s.getsockname()[1]; s.close()
+    return p
+
+
+def _worker(rank, world, port, out):
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, os.path.join(root, "gcn-song-embeddings_b200"))
+    import ps_dist
+    os.environ.update(RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank), MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    r, w, _ = ps_dist.init_from_env(backend="gloo")
+    assert (r, w) == (rank, world)
+    # gradient mean-allreduce on a flat buffer
+    flat = torch.full((1000,), float(rank + 1))
+    ps_dist.allreduce_mean_(flat, world)
+    assert torch.allclose(flat, torch.full((1000,), 1.5))
+    # parameter broadcast from rank 0
+    lin = torch.nn.Linear(4, 3)
+    with torch.no_grad():
+        lin.weight.fill_(float(rank)); lin.bias.fill_(float(rank))
+    ps_dist.broadcast_parameters(lin)
+    assert float(lin.weight.abs().sum()) == 0.0
+    # a replica pair stays in lock-step: same params + averaged grads -> same Adam update
+    torch.manual_seed(0)
+    model = torch.nn.Linear(8, 2)
+    ps_dist.broadcast_parameters(model)
+    opt = torch.optim.Adam(model.parameters(), lr=1e-2)
+    torch.manual_seed(100 + rank)  # rank-seeded batches differ
+    x = torch.randn(16, 8)
+    model(x).pow(2).mean().backward()
+    flat = torch.cat([p.grad.reshape(-1) for p in model.parameters()])
+    ps_dist.allreduce_mean_(flat, world)
+    off = 0
+    for p in model.parameters():
+        p.grad.copy_(flat[off: off + p.numel()].view_as(p)); off += p.numel()
+    opt.step()
+    gathered = [torch.zeros_like(model.weight) for _ in range(world)]
+    dist.all_gather(gathered, model.weight.data)
+    assert torch.equal(gathered[0], gathered[1])
+    # max-over-ranks timing and node-range shards
+    assert ps_dist.max_over_ranks(float(rank)) == float(world - 1)
+    lo, hi = ps_dist.shard_range(1001, rank, world)
+    sizes = torch.tensor([hi - lo]); dist.all_reduce(sizes)
+    assert int(sizes) == 1001 and (lo == 0 if rank == 0 else lo == 501)
+    ps_dist.barrier()
+    out.put(rank)
+    dist.destroy_process_group()
+
+
+def test_data_parallel_host_logic_world2():
+    ctx = mp.get_context("spawn")
+    out = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, out)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    assert sorted(out.get(timeout=5) for _ in range(2)) == [0, 1]
+
+
+def test_shard_range_covers_everything():
+    import ps_dist
+    for n in (0, 1, 7, 20_000_000):
+        for w in (1, 2, 8):
+            r = [ps_dist.shard_range(n, k, w) for k in range(w)]
+            assert r[0][0] == 0 and r[-1][1] == n
+            assert all(r[k][1] == r[k + 1][0] for k in range(w - 1))
