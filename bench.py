@@ -273,7 +273,9 @@ def run_ours(args, wl):
     w0 = time.perf_counter()
     t0.record()
     for _ in range(args.steps):
+        torch.cuda.nvtx.range_push("ps_step")  # lets `ncu --nvtx --nvtx-include "ps_step/"` isolate the timed steps
         loss, _, _ = device_step()
+        torch.cuda.nvtx.range_pop()
     t1.record()
     torch.cuda.synchronize(); ps_dist.barrier()
     wall = time.perf_counter() - w0

@@ -22,6 +22,20 @@ int ps_gemm_simt_launch(const float* P, int64_t ldp, int p_kmajor, const int32_t
                         const float* bias, int act, int l2norm, float* norm_out, int accumulate, int splits,
                         cudaStream_t stream);
 
+int ps_gemm_tc_launch(const float* P, int64_t ldp, int p_kmajor, const int32_t* p_rows,
+                      const float* Q, int64_t ldq, int q_kmajor, const int32_t* q_rows,
+                      float* C, int64_t ldc, int64_t M, int64_t N, int64_t K,
+                      const float* bias, int act, int l2norm, float* norm_out, int accumulate, int splits,
+                      cudaStream_t stream);
+
+static int g_gemm_backend = 0;  // 0 = tcgen05 3xTF32 where the shape allows, 1 = CUDA-core fp32 only
+
+extern "C" int ps_gemm_backend(int mode) {
+    const int old = g_gemm_backend;
+    if (mode == 0 || mode == 1) g_gemm_backend = mode;
+    return old;
+}
+
 extern "C" int ps_version(void) { return PS_ABI_VERSION; }
 extern "C" const char* ps_last_error(void) { return ps_err_buf(); }
 
@@ -35,6 +49,11 @@ extern "C" int ps_gemm(const float* P, int64_t ldp, int p_kmajor, const int32_t*
                        float* C, int64_t ldc, int64_t M, int64_t N, int64_t K,
                        const float* bias, int act, int l2norm, float* norm_out, int accumulate, int splits,
                        ps_stream_t stream) {
+    if (g_gemm_backend == 0) {
+        const int rc = ps_gemm_tc_launch(P, ldp, p_kmajor, p_rows, Q, ldq, q_kmajor, q_rows, C, ldc, M, N, K, bias, act, l2norm,
+                                         norm_out, accumulate, splits, static_cast<cudaStream_t>(stream));
+        if (rc != PS_ERR_UNSUPPORTED) return rc;
+    }
     return ps_gemm_simt_launch(P, ldp, p_kmajor, p_rows, Q, ldq, q_kmajor, q_rows, C, ldc, M, N, K, bias, act, l2norm,
                                norm_out, accumulate, splits, static_cast<cudaStream_t>(stream));
 }

@@ -27,6 +27,7 @@ _SIGNATURES = {
     "ps_version": ([], c_int),
     "ps_last_error": ([], c_char_p),
     "ps_set_device": ([c_int], c_int),
+    "ps_gemm_backend": ([c_int], c_int),
     "ps_graph_create": ([c_void_p, c_void_p, c_int64, c_int64, c_int64, ctypes.POINTER(c_void_p), c_void_p], c_int),
     "ps_graph_destroy": ([c_void_p], c_int),
     "ps_walk_topt": ([c_void_p, c_void_p, c_int64, c_int, c_double, c_int, c_int, c_uint64,
@@ -234,6 +235,11 @@ def _gemm(P, Q, C, M, N, K, p_kmajor, q_kmajor, p_rows, q_rows, bias, act, l2nor
                         _p(Q, torch.float32), _ld(Q), int(q_kmajor), _p(q_rows, torch.int32),
                         _p(C, torch.float32), _ld(C), int(M), int(N), int(K), _p(bias, torch.float32),
                         int(act), int(l2norm), _p(norm_out, torch.float32), int(accumulate), int(splits), _stream()))
+
+
+def gemm_backend(mode: int) -> int:
+    """0 = tcgen05 3xTF32 (default), 1 = CUDA-core fp32; returns the previous mode."""
+    return lib().ps_gemm_backend(int(mode))
 
 
 def aggregate_fwd(hin, self_rows, din, z, nbz, nbw, dh, cat, inv_wsum, tag="aggregate_fwd"):

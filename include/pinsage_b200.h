@@ -79,6 +79,11 @@ int ps_gemm(const float* P, int64_t ldp, int p_kmajor, const int32_t* p_rows,
             const float* bias, int act, int l2norm, float* norm_out, int accumulate, int splits,
             ps_stream_t stream);
 
+/* Select the ps_gemm implementation: 0 (default) = tcgen05 tensor cores with the 3xTF32
+ * error-compensated split wherever the shape allows (CUDA cores otherwise), 1 = CUDA-core
+ * fp32 only.  Returns the previous mode (any other argument just queries). */
+int ps_gemm_backend(int mode);
+
 /* ---- K4+K6: neighbour gather + importance-weighted mean fused with the concat
  *      (pinsage_model.py:195-197,202,208):
  *        cat[i, 0:din]       = hin[self_rows[i], 0:din]
