@@ -5,11 +5,11 @@
 // reference's fp32 parity (<= 1e-4) that plain TF32 cannot.
 //
 // Structure of one CTA (one 128 x BN output tile, BN = 128 or 256, optional split-K):
-//   warps 8-11 producers: LDG.128 the operand rows (row gather folded in, K4), split each
+//   warps 8-15 producers: LDG.128 the operand rows (row gather folded in, K4), split each
 //              fp32 into hi/lo, STS.128 into the UMMA canonical shared-memory layout
 //              (SWIZZLE_128B K-major or SWIZZLE_128B_BASE32B MN-major), fence.proxy.async,
 //              arrive on the stage's mbarrier;
-//   warp 12    lane 0 issues tcgen05.mma.cta_group::1.kind::tf32 (M=128, N=BN, K=8), 12 per
+//   warp 16    lane 0 issues tcgen05.mma.cta_group::1.kind::tf32 (M=128, N=BN, K=8), 12 per
 //              32-wide k-block, into one of two TMEM accumulators; tcgen05.commit frees the
 //              smem stage and, every 2 k-blocks, publishes the accumulator;
 //   warps 0-7  tcgen05.ld the finished accumulator (32x32b, one output row x BN/2 columns per
@@ -17,7 +17,8 @@
 //              (measured ~2e-8 relative per MMA, biased), so the truncating chain is kept to
 //              24 MMAs and the long sum is round-to-nearest; then the epilogue from registers:
 //              bias + leaky_relu + row L2-normalise and store, or red.global.add for split-K
-//              weight gradients.  Registers are rebalanced with setmaxnreg (184 / 88 / 40).
+//              weight gradients.  Registers are rebalanced with setmaxnreg (168 / 56 / 32 of the 96 per thread the CTA is launched with: the
+//              pool only holds what the CTA's own warps give back).
 // Replaces nn.Linear / AddmmBackward of ConvLayer and the head (pinsage_model.py:201,
 // 208-210, 259).
 #include "common.cuh"
@@ -27,8 +28,8 @@ namespace {
 
 constexpr int BM = 128;                 // UMMA M
 constexpr int BK = 32;                  // floats per k-block = one 128-byte swizzle row
-constexpr int kProducerThreads = 128;
-constexpr int kThreads = 512;
+constexpr int kProducerThreads = 256;
+constexpr int kThreads = 640;
 constexpr uint32_t kHiMask = 0xFFFFE000u;  // keep sign, exponent and the 10 tf32 mantissa bits
 
 struct TcArgs {
@@ -38,7 +39,8 @@ struct TcArgs {
     int64_t M, N, K;
     const float* bias; float* norm_out;
     int act, l2norm, accumulate;
-    int kb_per_split;  // k-blocks (of BK) per blockIdx.z
+    int kb_per_split;   // k-blocks (of BK) per split
+    int64_t mt, nt, zs;  // work grid: M tiles x N tiles x K splits
 };
 
 // ---------------------------------------------------------------- PTX wrappers
@@ -61,7 +63,7 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     if (mbar_try_wait(bar, parity)) return;
     const long long t0 = clock64();
     while (!mbar_try_wait(bar, parity)) {
-        if (clock64() - t0 > 4000000000ll) { printf("ps_gemm_tc: mbarrier timeout (block %d,%d,%d thread %d)\n", blockIdx.x, blockIdx.y, blockIdx.z, threadIdx.x); __trap(); }
+        if (clock64() - t0 > 2000000000ll) __trap();
     }
 }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
@@ -124,68 +126,114 @@ __device__ __forceinline__ void split_store(uint8_t* hi_base, uint8_t* lo_base, 
     *reinterpret_cast<float4*>(lo_base + off) = l;
 }
 
-// Fill one [ROWS x 32] operand tile (hi and lo copies) for the k-block starting at k0.
+// Producer-side view of one operand: everything that does not change from k-block to k-block is resolved
+// once per tile (row gather, row clamping, swizzled shared-memory offsets), so the per-k-block work of a
+// thread is LDG.128 + hi/lo split + 2 x STS.128 per float4 and nothing else.
 //   KMAJOR : element(i, r) = X[row(i)*ld + r]; SWIZZLE_128B: smem row i = 128 B, 16-B chunk c stored at c ^ (i % 8),
-//            8-row groups 1024 B apart (SBO)
+//            8-row groups 1024 B apart (SBO).  Thread t owns chunk c = t % 8 of rows (t / 8) + 32 j.
 //   MNMAJOR: element(i, r) = X[row(r)*ld + i]; SWIZZLE_128B_BASE32B: atoms of 4 k-rows x 32 i (512 B), 32-B chunk c
 //            of k-row r stored at c ^ (r % 4); atoms of consecutive i-chunks 512 B apart (LBO), 4-row k-groups
-//            (ROWS/32)*512 B apart (SBO)
-// Loads are issued in batches of 8 x LDG.128 per thread before the first use (memory-level parallelism).
-template <bool KMAJOR, int ROWS>
-__device__ __forceinline__ void fill_tile(uint8_t* hi, uint8_t* lo, const float* __restrict__ X, int64_t ld,
-                                          const int32_t* __restrict__ rows, int64_t i0, int64_t ext_i,
-                                          int64_t k0, int64_t k_end, int t) {
-    constexpr int BATCH = 8;
-    if (KMAJOR) {
-        const int c = t & 7;
-        const int64_t k = k0 + c * 4;
+//            (ROWS/32)*512 B apart (SBO).  Thread t owns float4 c4 = t % (ROWS/4) of k-rows t / (ROWS/4) + RPP j.
+// Rows / columns beyond the matrix edge are clamped to the last valid one: they only feed output rows /
+// columns that are never stored.  Only the contraction tail (k >= K) must read as zero.
+template <bool KMAJOR, int ROWS, bool PRECOMP>
+struct Operand {
+    static constexpr int NJ = KMAJOR ? ROWS / 32 : (BK * ROWS / 4) / kProducerThreads;  // float4 per thread per k-block
+    static constexpr int C4 = ROWS / 4;
+    static constexpr int RPP = kProducerThreads / C4;  // MN-major: k-rows per pass
+    // K-major + PRECOMP: one resolved pointer per owned row (row gather / clamp done once per tile).
+    // K-major, !PRECOMP: row pointers are rebuilt per k-block from (row0, ext, ld) -- 3 instructions, no registers.
+    // MN-major: one column base pointer; the row is the contraction index.
+    const float* base[(KMAJOR && PRECOMP) ? NJ : 1];
+    const int32_t* rows;  // MN-major: optional gather on the contraction index
+    int64_t ld;
+    int row0, ext;        // K-major, !PRECOMP
+    uint32_t off0;        // smem byte offset of the j = 0 element
+    int kq;               // K-major: first k of this thread inside a k-block; MN-major: first k-row
+
+    __device__ __forceinline__ void init(const float* X, int64_t ld_, const int32_t* rows_, int64_t i0, int64_t ext_i, int t) {
+        ld = ld_;
+        if (KMAJOR) {
+            const int c = t & 7, tr = t >> 3;
+            kq = c * 4;
+            rows = nullptr;
+            if (PRECOMP) {
 #pragma unroll
-        for (int p0 = 0; p0 < ROWS / 16; p0 += BATCH) {
-            float4 v[BATCH];
-#pragma unroll
-            for (int b = 0; b < BATCH; ++b) {
-                const int64_t i = i0 + (p0 + b) * 16 + (t >> 3);
-                v[b] = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (i < ext_i && k < k_end) {
-                    const int64_t row = rows ? static_cast<int64_t>(__ldg(rows + i)) : i;
-                    v[b] = ps_ldg4(X + row * ld + k);
+                for (int j = 0; j < NJ; ++j) {
+                    int64_t i = i0 + tr + 32 * j;
+                    if (i >= ext_i) i = ext_i - 1;
+                    const int64_t row = rows_ ? static_cast<int64_t>(__ldg(rows_ + i)) : i;
+                    base[j] = X + row * ld_ + kq;
                 }
+            } else {
+                base[0] = X + kq;
+                row0 = static_cast<int>(i0) + tr;
+                ext = static_cast<int>(ext_i);
             }
-#pragma unroll
-            for (int b = 0; b < BATCH; ++b) {
-                const int r = (p0 + b) * 16 + (t >> 3);
-                split_store(hi, lo, (r >> 3) * 1024 + (r & 7) * 128 + ((c ^ (r & 7)) << 4), v[b]);
-            }
+            off0 = (tr >> 3) * 1024 + (tr & 7) * 128 + ((c ^ (tr & 7)) << 4);
+        } else {
+            const int c4 = t % C4, tk = t / C4;
+            kq = tk;
+            rows = rows_;
+            int64_t i = i0 + c4 * 4;
+            if (i >= ext_i) i = 0;
+            base[0] = X + i;
+            off0 = (tk >> 2) * (ROWS / 32) * 512 + (c4 >> 3) * 512 + (tk & 3) * 128 + ((((c4 & 7) >> 1) ^ (tk & 3)) << 5) + ((c4 & 1) << 4);
         }
-    } else {
-        constexpr int C4 = ROWS / 4;               // float4 per k-row
-        constexpr int RPP = kProducerThreads / C4;  // k-rows per pass
-        const int c4 = t % C4;
-        const int64_t i = i0 + c4 * 4;
+    }
+    // byte distance in smem between the j-th and (j+1)-th element of this thread
+    static constexpr uint32_t kStep = KMAJOR ? 4096u : (RPP / 4) * (ROWS / 32) * 512u;
+
+    // load + split + store elements [J0, J0 + CNT) of this thread for the k-block at k0
+    template <int J0, int CNT>
+    __device__ __forceinline__ void load(float4 (&v)[CNT], int64_t k0, int64_t K) const {
+        if (KMAJOR) {
+            const bool ok = k0 + kq < K;
 #pragma unroll
-        for (int p0 = 0; p0 < BK / RPP; p0 += BATCH) {
-            float4 v[BATCH];
-#pragma unroll
-            for (int b = 0; b < BATCH; ++b) {
-                const int64_t k = k0 + (p0 + b) * RPP + t / C4;
-                v[b] = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (i < ext_i && k < k_end) {
-                    const int64_t row = rows ? static_cast<int64_t>(__ldg(rows + k)) : k;
-                    v[b] = ps_ldg4(X + row * ld + i);
+            for (int j = 0; j < CNT; ++j) {
+                v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (ok) {
+                    if (PRECOMP) v[j] = ps_ldg4(base[J0 + j] + k0);
+                    else v[j] = ps_ldg4(base[0] + static_cast<int64_t>(min(row0 + 32 * (J0 + j), ext - 1)) * ld + k0);
                 }
             }
+        } else {
 #pragma unroll
-            for (int b = 0; b < BATCH; ++b) {
-                const int kr = (p0 + b) * RPP + t / C4;
-                split_store(hi, lo, (kr >> 2) * (ROWS / 32) * 512 + (c4 >> 3) * 512 + (kr & 3) * 128 +
-                                        ((((c4 & 7) >> 1) ^ (kr & 3)) << 5) + ((c4 & 1) << 4), v[b]);
+            for (int j = 0; j < CNT; ++j) {
+                const int64_t k = k0 + kq + RPP * (J0 + j);
+                v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (k < K) {
+                    const int64_t row = rows ? static_cast<int64_t>(__ldg(rows + k)) : k;
+                    v[j] = ps_ldg4(base[0] + row * ld);
+                }
             }
         }
     }
+    template <int J0, int CNT>
+    __device__ __forceinline__ void store(uint8_t* hi, uint8_t* lo, const float4 (&v)[CNT]) const {
+#pragma unroll
+        for (int j = 0; j < CNT; ++j) split_store(hi, lo, off0 + (J0 + j) * kStep, v[j]);
+    }
+};
+
+// One unit of work of the persistent kernel: a 128 x BN output tile over a range of k-blocks.
+struct Work {
+    int64_t m0, n0;
+    int kb_begin, num_kb;
+};
+__device__ __forceinline__ Work decode_work(const TcArgs& a, int64_t w, int bn) {
+    const int64_t n_idx = w % a.nt, rest = w / a.nt;
+    const int64_t m_idx = rest % a.mt, z = rest / a.mt;
+    const int64_t nkb = (a.K + BK - 1) / BK;
+    const int64_t b = z * a.kb_per_split;
+    const int64_t e = min(nkb, b + a.kb_per_split);
+    return {m_idx * BM, n_idx * static_cast<int64_t>(bn), static_cast<int>(b), static_cast<int>(e - b)};
 }
 
-// Thread roles (16 warps): 0-7 accumulate + epilogue, 8-11 producers, 12 MMA issue (13-15 only give their
-// registers away: setmaxnreg works on whole warpgroups).
+// Thread roles (20 warps): 0-7 accumulate + epilogue, 8-15 producers, 16 MMA issue (17-19 only give their
+// registers away: setmaxnreg works on whole warpgroups).  Persistent: every role walks the same list of work
+// items (blockIdx.x, + gridDim.x, ...), so the producers and the MMA warp run ahead into the next tile while
+// the accumulate warps are still storing the previous one.
 template <bool PK, bool QK, int BN>
 __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(TcArgs a) {
     constexpr int STAGES = BN == 256 ? 2 : 3;
@@ -197,139 +245,162 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(TcArgs a) {
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
-    float* ss_buf = reinterpret_cast<float*>(tmem_slot + 4);  // [2][128] partial sums of squares (l2norm)
+    float* ss_buf = reinterpret_cast<float*>(tmem_slot + 4);  // [2 parities][2 halves][128] partial sums of squares (l2norm)
+    float* bias_s = ss_buf + 2 * 2 * 128;                     // [2 parities][BN] bias of the current tile
     const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + STAGES);
     const uint32_t tfull0 = smem_u32(bars + 2 * STAGES), tempty0 = smem_u32(bars + 2 * STAGES + 2);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int64_t m0 = static_cast<int64_t>(blockIdx.x) * BM, n0 = static_cast<int64_t>(blockIdx.y) * BN;
-    const int64_t num_kb_total = (a.K + BK - 1) / BK;
-    const int64_t kb_begin = static_cast<int64_t>(blockIdx.z) * a.kb_per_split;
-    const int64_t kb_end = min(num_kb_total, kb_begin + a.kb_per_split);
-    const int num_kb = static_cast<int>(kb_end - kb_begin);
-    if (num_kb <= 0) return;  // uniform per CTA
-    const int n_chunks = (num_kb + CHUNK_KB - 1) / CHUNK_KB;
+    const int64_t total_work = a.mt * a.nt * a.zs;
 
     if (tid == 0) {
         for (int s = 0; s < STAGES; ++s) { mbar_init(full0 + 8 * s, kProducerThreads); mbar_init(empty0 + 8 * s, 1); }
         for (int b = 0; b < 2; ++b) { mbar_init(tfull0 + 8 * b, 1); mbar_init(tempty0 + 8 * b, 8); }
         fence_barrier_init();
     }
-    if (warp == 12) tmem_alloc<2 * BN>(smem_u32(tmem_slot));
+    if (warp == 16) tmem_alloc<2 * BN>(smem_u32(tmem_slot));
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    if (warp >= 12) {
-        asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
-        // ------------------------------------------------ MMA issue (one lane of warp 12)
-        if (warp == 12 && lane == 0) {
+    if (warp >= 16) {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 32;");
+        // ------------------------------------------------ MMA issue (one lane of warp 16)
+        if (warp == 16 && lane == 0) {
             constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((PK ? 0u : 1u) << 15) | ((QK ? 0u : 1u) << 16) |
                                        (static_cast<uint32_t>(BN >> 3) << 17) | (static_cast<uint32_t>(BM >> 4) << 24);
             constexpr uint32_t A_LBO = PK ? 16 : 512, A_SBO = PK ? 1024 : (BM / 32) * 512, A_STEP = PK ? 32 : 2 * (BM / 32) * 512;
             constexpr uint32_t B_LBO = QK ? 16 : 512, B_SBO = QK ? 1024 : (BN / 32) * 512, B_STEP = QK ? 32 : 2 * (BN / 32) * 512;
             constexpr uint32_t A_LAY = PK ? 2u : 1u, B_LAY = QK ? 2u : 1u;
             int stage = 0; uint32_t phase = 0;
-            int kb = 0;
-            for (int c = 0; c < n_chunks; ++c) {
-                const int buf = c & 1;
-                mbar_wait(tempty0 + 8 * buf, ((c >> 1) & 1) ^ 1);  // the drain of this buffer's previous chunk is done
-                tc_fence_after();
-                const uint32_t tacc = tmem_base + buf * BN;
-                for (int q = 0; q < CHUNK_KB && kb < num_kb; ++q, ++kb) {
-                    mbar_wait(full0 + 8 * stage, phase);
+            uint32_t gc = 0;  // chunks issued so far (selects the TMEM buffer and its barrier parity)
+            for (int64_t w = blockIdx.x; w < total_work; w += gridDim.x) {
+                const Work wk = decode_work(a, w, BN);
+                int kb = 0;
+                while (kb < wk.num_kb) {
+                    const uint32_t buf = gc & 1;
+                    mbar_wait(tempty0 + 8 * buf, ((gc >> 1) & 1) ^ 1);  // the drain of this buffer's previous chunk is done
                     tc_fence_after();
-                    const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
-                    const uint32_t a_hi = sa, a_lo = sa + A_BYTES, b_hi = sa + 2 * A_BYTES, b_lo = b_hi + B_BYTES;
+                    const uint32_t tacc = tmem_base + buf * BN;
+                    for (int q = 0; q < CHUNK_KB && kb < wk.num_kb; ++q, ++kb) {
+                        mbar_wait(full0 + 8 * stage, phase);
+                        tc_fence_after();
+                        const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
+                        const uint32_t a_hi = sa, a_lo = sa + A_BYTES, b_hi = sa + 2 * A_BYTES, b_lo = b_hi + B_BYTES;
 #pragma unroll
-                    for (int s = 0; s < BK / 8; ++s) {
-                        const uint64_t dah = make_desc(a_hi + s * A_STEP, A_LBO, A_SBO, A_LAY), dal = make_desc(a_lo + s * A_STEP, A_LBO, A_SBO, A_LAY);
-                        const uint64_t dbh = make_desc(b_hi + s * B_STEP, B_LBO, B_SBO, B_LAY), dbl = make_desc(b_lo + s * B_STEP, B_LBO, B_SBO, B_LAY);
-                        umma_tf32(tacc, dal, dbh, idesc, (q | s) != 0);  // a chunk starts a fresh accumulator; small terms first
-                        umma_tf32(tacc, dah, dbl, idesc, 1u);
-                        umma_tf32(tacc, dah, dbh, idesc, 1u);
+                        for (int s = 0; s < BK / 8; ++s) {
+                            const uint64_t dah = make_desc(a_hi + s * A_STEP, A_LBO, A_SBO, A_LAY), dal = make_desc(a_lo + s * A_STEP, A_LBO, A_SBO, A_LAY);
+                            const uint64_t dbh = make_desc(b_hi + s * B_STEP, B_LBO, B_SBO, B_LAY), dbl = make_desc(b_lo + s * B_STEP, B_LBO, B_SBO, B_LAY);
+                            umma_tf32(tacc, dal, dbh, idesc, (q | s) != 0);  // a chunk starts a fresh accumulator; small terms first
+                            umma_tf32(tacc, dah, dbl, idesc, 1u);
+                            umma_tf32(tacc, dah, dbh, idesc, 1u);
+                        }
+                        umma_commit(empty0 + 8 * stage);  // frees the smem stage once these MMAs have read it
+                        if (++stage == STAGES) { stage = 0; phase ^= 1; }
                     }
-                    umma_commit(empty0 + 8 * stage);  // frees the smem stage once these MMAs have read it
-                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                    umma_commit(tfull0 + 8 * buf);  // publishes the chunk to the accumulate warps
+                    ++gc;
                 }
-                umma_commit(tfull0 + 8 * buf);  // publishes the chunk to the accumulate warps
             }
         }
     } else if (warp >= 8) {
-        asm volatile("setmaxnreg.dec.sync.aligned.u32 88;");
-        // ------------------------------------------------ producers
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+        // ------------------------------------------------ producers (8 warps)
         const int t = tid - 8 * 32;
+        using OpA = Operand<PK, BM, true>;
+        using OpB = Operand<QK, BN, false>;
+        constexpr int HB = OpB::NJ / 2;
         int stage = 0; uint32_t phase = 0;
-        for (int kb = 0; kb < num_kb; ++kb) {
-            mbar_wait(empty0 + 8 * stage, phase ^ 1);
-            uint8_t* st = smem + stage * STAGE_BYTES;
-            const int64_t k0 = (kb_begin + kb) * BK;
-            fill_tile<PK, BM>(st, st + A_BYTES, a.P, a.ldp, a.p_rows, m0, a.M, k0, a.K, t);
-            fill_tile<QK, BN>(st + 2 * A_BYTES, st + 2 * A_BYTES + B_BYTES, a.Q, a.ldq, a.q_rows, n0, a.N, k0, a.K, t);
-            fence_proxy_async();  // generic-proxy smem writes -> visible to the tensor core's async proxy
-            mbar_arrive(full0 + 8 * stage);
-            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        for (int64_t w = blockIdx.x; w < total_work; w += gridDim.x) {
+            const Work wk = decode_work(a, w, BN);
+            OpA opa;
+            OpB opb;
+            opa.init(a.P, a.ldp, a.p_rows, wk.m0, a.M, t);
+            opb.init(a.Q, a.ldq, a.q_rows, wk.n0, a.N, t);
+            for (int kb = 0; kb < wk.num_kb; ++kb) {
+                const int64_t k0 = static_cast<int64_t>(wk.kb_begin + kb) * BK;
+                float4 va[OpA::NJ];
+                opa.template load<0, OpA::NJ>(va, k0, a.K);  // issued before the stage is free: the loads overlap the wait
+                float4 vb[HB];
+                opb.template load<0, HB>(vb, k0, a.K);
+                mbar_wait(empty0 + 8 * stage, phase ^ 1);
+                uint8_t* st = smem + stage * STAGE_BYTES;
+                opa.template store<0, OpA::NJ>(st, st + A_BYTES, va);
+                opb.template store<0, HB>(st + 2 * A_BYTES, st + 2 * A_BYTES + B_BYTES, vb);
+                opb.template load<HB, HB>(vb, k0, a.K);
+                opb.template store<HB, HB>(st + 2 * A_BYTES, st + 2 * A_BYTES + B_BYTES, vb);
+                fence_proxy_async();  // generic-proxy smem writes -> visible to the tensor core's async proxy
+                mbar_arrive(full0 + 8 * stage);
+                if (++stage == STAGES) { stage = 0; phase ^= 1; }
+            }
         }
     } else {
-        asm volatile("setmaxnreg.inc.sync.aligned.u32 184;");
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 168;");
         // ------------------------------------------------ accumulate (fp32, round-to-nearest, in registers) + epilogue
         // Each chunk of CHUNK_KB k-blocks (24 MMAs) is summed by the tensor core in TMEM, whose adder truncates;
         // draining it into registers keeps the truncating chain short (fp32-level accuracy).
         const int quarter = warp & 3, half = warp >> 2;
-        const int64_t row = m0 + quarter * 32 + lane;
         const uint32_t tlane = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + half * HALF;
+        uint32_t gc = 0, tile_par = 0;
         float acc[HALF];
+        for (int64_t w = blockIdx.x; w < total_work; w += gridDim.x, tile_par ^= 1) {
+            const Work wk = decode_work(a, w, BN);
+            const int n_chunks = (wk.num_kb + CHUNK_KB - 1) / CHUNK_KB;
 #pragma unroll
-        for (int j = 0; j < HALF; ++j) acc[j] = 0.f;
-        for (int c = 0; c < n_chunks; ++c) {
-            const int buf = c & 1;
-            mbar_wait(tfull0 + 8 * buf, (c >> 1) & 1);
-            tc_fence_after();
+            for (int j = 0; j < HALF; ++j) acc[j] = 0.f;
+            for (int c = 0; c < n_chunks; ++c, ++gc) {
+                const uint32_t buf = gc & 1;
+                mbar_wait(tfull0 + 8 * buf, (gc >> 1) & 1);
+                tc_fence_after();
 #pragma unroll
-            for (int q = 0; q < HALF / 16; ++q) {
-                uint32_t v[16];
-                tmem_ld16(tlane + buf * BN + q * 16, v);
+                for (int q = 0; q < HALF / 16; ++q) {
+                    uint32_t v[16];
+                    tmem_ld16(tlane + buf * BN + q * 16, v);
 #pragma unroll
-                for (int j = 0; j < 16; ++j) acc[q * 16 + j] += __uint_as_float(v[j]);
+                    for (int j = 0; j < 16; ++j) acc[q * 16 + j] += __uint_as_float(v[j]);
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(tempty0 + 8 * buf);
             }
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(tempty0 + 8 * buf);
-        }
-        // epilogue on this thread's [row, n0 + half*HALF .. +HALF)
-        const int64_t col0 = n0 + half * HALF;
-        const bool row_ok = row < a.M;
-        float ss = 0.f;
-#pragma unroll
-        for (int j = 0; j < HALF; ++j) {
-            const int64_t col = col0 + j;
-            if (col < a.N) {
-                float x = acc[j] + (a.bias ? __ldg(a.bias + col) : 0.f);
-                if (a.act == 1) x = ps_leaky(x);
-                acc[j] = x;
-                ss = fmaf(x, x, ss);
-            }
-        }
-        float inv_norm = 1.f;
-        if (a.l2norm) {  // the row is split over two threads (column halves): combine through shared memory
-            ss_buf[half * 128 + quarter * 32 + lane] = ss;
+            // ---- epilogue on this thread's [row, n0 + half*HALF .. +HALF); the MMA warp is already on the next tile
+            const int64_t row = wk.m0 + quarter * 32 + lane;
+            const int64_t col0 = wk.n0 + half * HALF;
+            const bool row_ok = row < a.M;
+            float* bs = bias_s + tile_par * BN;
+            if (tid < BN) bs[tid] = (a.bias != nullptr && wk.n0 + tid < a.N) ? __ldg(a.bias + wk.n0 + tid) : 0.f;
             asm volatile("bar.sync 1, 256;" ::: "memory");
-            const float nrm = sqrtf(ss_buf[quarter * 32 + lane] + ss_buf[128 + quarter * 32 + lane]);
-            inv_norm = 1.f / nrm;
-            if (half == 0 && row_ok && a.norm_out) a.norm_out[row] = nrm;
-        }
-        if (row_ok) {
-            float* dst = a.C + row * a.ldc + col0;
+            const float slope = a.act == 1 ? PS_LEAKY_SLOPE : 1.f;
+            float ss = 0.f;
 #pragma unroll
-            for (int j = 0; j < HALF; j += 4) {
-                if (col0 + j < a.N) {  // N % 4 == 0: a float4 is all-or-nothing
-                    if (a.accumulate) {
-                        atomicAdd(dst + j + 0, acc[j + 0]); atomicAdd(dst + j + 1, acc[j + 1]);
-                        atomicAdd(dst + j + 2, acc[j + 2]); atomicAdd(dst + j + 3, acc[j + 3]);
-                    } else {
-                        *reinterpret_cast<float4*>(dst + j) = make_float4(acc[j] * inv_norm, acc[j + 1] * inv_norm,
-                                                                          acc[j + 2] * inv_norm, acc[j + 3] * inv_norm);
+            for (int j = 0; j < HALF; ++j) {
+                float x = acc[j] + bs[half * HALF + j];
+                x = x > 0.f ? x : x * slope;
+                acc[j] = x;
+                ss = fmaf(x, (col0 + j < a.N) ? x : 0.f, ss);
+            }
+            float inv_norm = 1.f;
+            if (a.l2norm) {  // the row is split over two threads (column halves): combine through shared memory
+                float* sb = ss_buf + tile_par * 256;
+                sb[half * 128 + quarter * 32 + lane] = ss;
+                asm volatile("bar.sync 1, 256;" ::: "memory");
+                const float nrm = sqrtf(sb[quarter * 32 + lane] + sb[128 + quarter * 32 + lane]);
+                inv_norm = 1.f / nrm;
+                if (half == 0 && row_ok && a.norm_out) a.norm_out[row] = nrm;
+            }
+            if (row_ok) {
+                float* dst = a.C + row * a.ldc + col0;
+#pragma unroll
+                for (int j = 0; j < HALF; j += 4) {
+                    if (col0 + j < a.N) {  // N % 4 == 0: a float4 is all-or-nothing
+                        if (a.accumulate) {
+                            atomicAdd(dst + j + 0, acc[j + 0]); atomicAdd(dst + j + 1, acc[j + 1]);
+                            atomicAdd(dst + j + 2, acc[j + 2]); atomicAdd(dst + j + 3, acc[j + 3]);
+                        } else {
+                            *reinterpret_cast<float4*>(dst + j) = make_float4(acc[j] * inv_norm, acc[j + 1] * inv_norm,
+                                                                              acc[j + 2] * inv_norm, acc[j + 3] * inv_norm);
+                        }
                     }
                 }
             }
@@ -337,19 +408,25 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(TcArgs a) {
         tc_fence_before();
     }
     __syncthreads();
-    if (warp == 12) { tc_fence_after(); tmem_dealloc<2 * BN>(tmem_base); }
+    if (warp == 16) { tc_fence_after(); tmem_dealloc<2 * BN>(tmem_base); }
 }
 
 template <bool PK, bool QK, int BN>
-int launch_tc(const TcArgs& a, dim3 grid, cudaStream_t stream) {
+int launch_tc(const TcArgs& a, cudaStream_t stream) {
     constexpr int STAGES = BN == 256 ? 2 : 3;
-    constexpr size_t smem = STAGES * (2 * BM * 128 + 2 * BN * 128) + (2 * STAGES + 4) * 8 + 16 + 2 * 128 * 4 + 1024;
+    constexpr size_t smem = STAGES * (2 * BM * 128 + 2 * BN * 128) + (2 * STAGES + 4) * 8 + 16 + (2 * 2 * 128 + 2 * BN) * 4 + 1024;
     auto kern = gemm_tc_kernel<PK, QK, BN>;
     static bool configured = false;
+    static int sms = 148;
     if (!configured) {
         PS_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+        int dev = 0;
+        PS_CUDA_CHECK(cudaGetDevice(&dev));
+        PS_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
         configured = true;
     }
+    const int64_t total = a.mt * a.nt * a.zs;
+    const unsigned grid = static_cast<unsigned>(total < sms ? total : sms);  // persistent: one CTA per SM
     kern<<<grid, kThreads, smem, stream>>>(a);
     PS_LAUNCH_CHECK();
     return PS_OK;
@@ -370,6 +447,7 @@ int ps_gemm_tc_launch(const float* P, int64_t ldp, int p_kmajor, const int32_t* 
     if (!p_kmajor && M % 4 != 0) return PS_ERR_UNSUPPORTED;
     if ((reinterpret_cast<uintptr_t>(P) | reinterpret_cast<uintptr_t>(Q) | reinterpret_cast<uintptr_t>(C)) % 16 != 0) return PS_ERR_UNSUPPORTED;
     if (l2norm && N > 256) return PS_ERR_UNSUPPORTED;
+    if (q_kmajor && q_rows) return PS_ERR_UNSUPPORTED;  // row pointers of Q are not precomputed
     if (accumulate && (bias || act || l2norm)) return PS_ERR_UNSUPPORTED;
     if (splits > 1 && !accumulate) return PS_ERR_UNSUPPORTED;
     // The tensor core's TMEM accumulator truncates on every add (measured: ~2e-8 relative per MMA, biased
@@ -380,16 +458,16 @@ int ps_gemm_tc_launch(const float* P, int64_t ldp, int p_kmajor, const int32_t* 
     if (!accumulate && K > 4 * kMaxChainK) return PS_ERR_UNSUPPORTED;
     if (accumulate && ps_ceil_div(K, splits < 1 ? 1 : splits) > kMaxChainK) splits = static_cast<int>(ps_ceil_div(K, kMaxChainK));
     const int BN = (N > 128) ? 256 : 128;
-    TcArgs a{P, ldp, p_rows, Q, ldq, q_rows, C, ldc, M, N, K, bias, norm_out, act, l2norm, accumulate, 0};
+    TcArgs a{P, ldp, p_rows, Q, ldq, q_rows, C, ldc, M, N, K, bias, norm_out, act, l2norm, accumulate, 0, 0, 0, 0};
     const int64_t num_kb = ps_ceil_div(K, BK);
     if (splits < 1) splits = 1;
     a.kb_per_split = static_cast<int>(ps_ceil_div(num_kb, splits));
-    const int64_t zs = ps_ceil_div(num_kb, a.kb_per_split);
-    dim3 grid(static_cast<unsigned>(ps_ceil_div(M, BM)), static_cast<unsigned>(ps_ceil_div(N, BN)), static_cast<unsigned>(zs));
-    if (grid.y > 65535u || grid.z > 65535u) return PS_ERR_UNSUPPORTED;
+    a.zs = ps_ceil_div(num_kb, a.kb_per_split);
+    a.mt = ps_ceil_div(M, BM);
+    a.nt = ps_ceil_div(N, BN);
 #define PS_TC_CASE(pk, qk)                                                         \
     if (static_cast<bool>(p_kmajor) == pk && static_cast<bool>(q_kmajor) == qk)     \
-        return BN == 256 ? launch_tc<pk, qk, 256>(a, grid, stream) : launch_tc<pk, qk, 128>(a, grid, stream);
+        return BN == 256 ? launch_tc<pk, qk, 256>(a, stream) : launch_tc<pk, qk, 128>(a, stream);
     PS_TC_CASE(true, true)
     PS_TC_CASE(true, false)
     PS_TC_CASE(false, true)
