@@ -80,17 +80,32 @@ aggregate_fwd_kernel(const float* __restrict__ hin, int64_t ld_hin, const int32_
     if (lane == 0) inv_wsum[i] = inv;
 }
 
-// z[u,:] = leaky'(z[u,:]) * sum_{q in seg(u)} w[q] * inv_wsum[q/T] * dcat[q/T, col_off:col_off+dh]
+// Backward of the aggregation as a load-balanced segmented gather.  Z-row u receives
+//   z[u,:] = leaky'(z[u,:]) * sum_{q in seg(u)} w[q] * inv_wsum[q/T] * dcat[q/T, col_off:col_off+dh]
+// Popular nodes own segments of 10^4+ pairs while most rows own a handful, so the work unit is a CHUNK of at
+// most `chunk_pairs` consecutive pairs of one segment (one warp each, chunk_off[u] = first chunk of row u).
+// A row with a single chunk is finished in place; a row with several chunks writes raw partial sums to a
+// scratch buffer that aggregate_bwd_reduce_kernel then folds (no atomics: the result is deterministic).
 template <int CH>
 __global__ void __launch_bounds__(kWarps * 32)
 aggregate_bwd_kernel(const float* __restrict__ dcat, int64_t ldcat, int col_off, int dh,
-                     const int32_t* __restrict__ seg_off, const int32_t* __restrict__ pair_q,
-                     const float* __restrict__ nbw, const float* __restrict__ inv_wsum, int T,
-                     float* __restrict__ z, int64_t ldz, int64_t n_zrows) {
+                     const int32_t* __restrict__ seg_off, const int32_t* __restrict__ chunk_off, int chunk_pairs,
+                     const int32_t* __restrict__ pair_q, const float* __restrict__ nbw,
+                     const float* __restrict__ inv_wsum, int T,
+                     float* __restrict__ z, int64_t ldz, int64_t n_zrows, float* __restrict__ partial) {
     const int lane = threadIdx.x & 31;
-    const int64_t u = static_cast<int64_t>(blockIdx.x) * kWarps + (threadIdx.x >> 5);
-    if (u >= n_zrows) return;
-    const int beg = __ldg(seg_off + u), end = __ldg(seg_off + u + 1);
+    const int64_t chunk = static_cast<int64_t>(blockIdx.x) * kWarps + (threadIdx.x >> 5);
+    if (chunk >= __ldg(chunk_off + n_zrows)) return;
+    // row that owns this chunk: the last u with chunk_off[u] <= chunk
+    int64_t lo = 0, hi = n_zrows;
+    while (hi - lo > 1) {
+        const int64_t mid = (lo + hi) >> 1;
+        if (__ldg(chunk_off + mid) <= chunk) lo = mid; else hi = mid;
+    }
+    const int64_t u = lo;
+    const int first = __ldg(chunk_off + u), n_chunks = __ldg(chunk_off + u + 1) - first;
+    const int beg = __ldg(seg_off + u) + static_cast<int>(chunk - first) * chunk_pairs;
+    const int end = min(__ldg(seg_off + u + 1), beg + chunk_pairs);
     float4 acc[CH];
 #pragma unroll
     for (int c = 0; c < CH; ++c) acc[c] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -131,6 +146,53 @@ aggregate_bwd_kernel(const float* __restrict__ dcat, int64_t ldcat, int col_off,
                 const float4 v = ps_ldg4(dcat + row * ldcat + col_off + col);
                 acc[c].x = fmaf(coef, v.x, acc[c].x); acc[c].y = fmaf(coef, v.y, acc[c].y);
                 acc[c].z = fmaf(coef, v.z, acc[c].z); acc[c].w = fmaf(coef, v.w, acc[c].w);
+            }
+        }
+    }
+    if (n_chunks == 1) {
+        float* zr = z + u * ldz;
+#pragma unroll
+        for (int c = 0; c < CH; ++c) {
+            const int col = (c * 32 + lane) * 4;
+            if (col < dh) {
+                const float4 y = *reinterpret_cast<const float4*>(zr + col);
+                *reinterpret_cast<float4*>(zr + col) =
+                    make_float4(acc[c].x * ps_leaky_grad_from_out(y.x), acc[c].y * ps_leaky_grad_from_out(y.y),
+                                acc[c].z * ps_leaky_grad_from_out(y.z), acc[c].w * ps_leaky_grad_from_out(y.w));
+            }
+        }
+    } else {
+        float* pr = partial + chunk * dh;
+#pragma unroll
+        for (int c = 0; c < CH; ++c) {
+            const int col = (c * 32 + lane) * 4;
+            if (col < dh) *reinterpret_cast<float4*>(pr + col) = acc[c];
+        }
+    }
+}
+
+// Second pass: rows with no pair get a zero gradient, rows split over several chunks get the sum of their
+// partials (in chunk order) times leaky'(z).  Rows with exactly one chunk were finished by the first pass.
+template <int CH>
+__global__ void __launch_bounds__(kWarps * 32)
+aggregate_bwd_reduce_kernel(const int32_t* __restrict__ chunk_off, const float* __restrict__ partial, int dh,
+                            float* __restrict__ z, int64_t ldz, int64_t n_zrows) {
+    const int lane = threadIdx.x & 31;
+    const int64_t u = static_cast<int64_t>(blockIdx.x) * kWarps + (threadIdx.x >> 5);
+    if (u >= n_zrows) return;
+    const int first = __ldg(chunk_off + u), n_chunks = __ldg(chunk_off + u + 1) - first;
+    if (n_chunks == 1) return;
+    float4 acc[CH];
+#pragma unroll
+    for (int c = 0; c < CH; ++c) acc[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int k = 0; k < n_chunks; ++k) {
+        const float* pr = partial + static_cast<int64_t>(first + k) * dh;
+#pragma unroll
+        for (int c = 0; c < CH; ++c) {
+            const int col = (c * 32 + lane) * 4;
+            if (col < dh) {
+                const float4 v = ps_ldg4(pr + col);
+                acc[c].x += v.x; acc[c].y += v.y; acc[c].z += v.z; acc[c].w += v.w;
             }
         }
     }
@@ -271,16 +333,24 @@ extern "C" int ps_aggregate_fwd(const float* hin, int64_t ld_hin, const int32_t*
 }
 
 extern "C" int ps_aggregate_bwd(const float* dcat, int64_t ldcat, int col_off, int dh, const int32_t* seg_off,
+                                const int32_t* chunk_off, int chunk_pairs, int64_t max_chunks,
                                 const int32_t* pair_q, const float* nbw, const float* inv_wsum, int T,
-                                float* z, int64_t ldz, int64_t n_zrows, ps_stream_t stream_) {
+                                float* z, int64_t ldz, int64_t n_zrows, float* partial_ws, ps_stream_t stream_) {
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-    PS_REQUIRE(dcat && seg_off && pair_q && nbw && inv_wsum && z, "null pointer");
+    PS_REQUIRE(dcat && seg_off && chunk_off && pair_q && nbw && inv_wsum && z && partial_ws, "null pointer");
     PS_REQUIRE(dh > 0 && dh % 4 == 0 && col_off % 4 == 0 && ldcat % 4 == 0 && ldz % 4 == 0 && T > 0, "bad shape");
     PS_REQUIRE(dh <= 1024, "hidden dim > 1024 not supported");
+    PS_REQUIRE(chunk_pairs > 0 && max_chunks >= 0, "bad chunking");
     if (n_zrows == 0) return PS_OK;
-    const unsigned blocks = static_cast<unsigned>(ps_ceil_div(n_zrows, kWarps));
-    PS_DISPATCH_CH(dh, (aggregate_bwd_kernel<CH><<<blocks, kWarps * 32, 0, stream>>>(
-                           dcat, ldcat, col_off, dh, seg_off, pair_q, nbw, inv_wsum, T, z, ldz, n_zrows)));
+    if (max_chunks > 0) {
+        const unsigned blocks = static_cast<unsigned>(ps_ceil_div(max_chunks, kWarps));
+        PS_DISPATCH_CH(dh, (aggregate_bwd_kernel<CH><<<blocks, kWarps * 32, 0, stream>>>(
+                               dcat, ldcat, col_off, dh, seg_off, chunk_off, chunk_pairs, pair_q, nbw, inv_wsum, T, z, ldz,
+                               n_zrows, partial_ws)));
+        PS_LAUNCH_CHECK();
+    }
+    const unsigned rblocks = static_cast<unsigned>(ps_ceil_div(n_zrows, kWarps));
+    PS_DISPATCH_CH(dh, (aggregate_bwd_reduce_kernel<CH><<<rblocks, kWarps * 32, 0, stream>>>(chunk_off, partial_ws, dh, z, ldz, n_zrows)));
     PS_LAUNCH_CHECK();
     return PS_OK;
 }

@@ -73,6 +73,7 @@ class LayerPlan:
     zrows: Optional[torch.Tensor]  # int32 [nz] gather index into the feature table (layer 0) or None
     seg_off: Optional[torch.Tensor] = None  # int32 [nz+1]  (backward)
     pair_q: Optional[torch.Tensor] = None   # int32 [n*T]   (backward)
+    chunk_off: Optional[torch.Tensor] = None  # int32 [nz+1] first work chunk of every z-row (backward)
 
 
 @dataclass
@@ -114,6 +115,7 @@ def build_plan(top: torch.Tensor, n_layers: int, T: int, table: NeighborTable, n
             seg = torch.zeros(nz + 1, dtype=torch.int32, device=flat.device)
             seg[1:] = torch.cumsum(torch.bincount(flat, minlength=nz), 0)
             lp.seg_off = seg
+            lp.chunk_off = nat.aggregate_bwd_chunks(seg)
         plan.layers[l] = lp
         cur = nxt
     return plan
@@ -218,7 +220,7 @@ class Engine:
             nat.colsum(d_pre, grads[pre + "W.bias"])
             d_cat = torch.empty((lp.n, din + dh), dtype=torch.float32, device="cuda")
             nat.gemm(d_pre, conv.W.weight, d_cat, lp.n, din + dh, do, q_kmajor=False, tag=f"gemm_w_dgrad_l{l}")
-            nat.aggregate_bwd(d_cat, din, dh, lp.seg_off, lp.pair_q, lp.w, inv_wsum, lp.w.shape[1], z, tag=f"aggregate_bwd_l{l}")  # z := dZ_pre
+            nat.aggregate_bwd(d_cat, din, dh, lp.seg_off, lp.pair_q, lp.w, inv_wsum, lp.w.shape[1], z, chunk_off=lp.chunk_off, tag=f"aggregate_bwd_l{l}")  # z := dZ_pre
             nat.gemm(z, h_in, grads[pre + "Q.weight"], dh, din, lp.nz, p_kmajor=False, q_kmajor=False,
                      q_rows=lp.zrows, accumulate=True, splits=_splits_for(dh, din, lp.nz), tag=f"gemm_q_wgrad_l{l}")
             nat.colsum(z, grads[pre + "Q.bias"])

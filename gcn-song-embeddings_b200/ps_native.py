@@ -37,8 +37,8 @@ _SIGNATURES = {
                  c_int64, c_int64, c_int64, c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_void_p], c_int),
     "ps_aggregate_fwd": ([c_void_p, c_int64, c_void_p, c_int, c_void_p, c_int64, c_void_p, c_void_p, c_int, c_int,
                           c_int64, c_void_p, c_int64, c_void_p, c_void_p], c_int),
-    "ps_aggregate_bwd": ([c_void_p, c_int64, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int,
-                          c_void_p, c_int64, c_int64, c_void_p], c_int),
+    "ps_aggregate_bwd": ([c_void_p, c_int64, c_int, c_int, c_void_p, c_void_p, c_int, c_int64, c_void_p, c_void_p,
+                          c_void_p, c_int, c_void_p, c_int64, c_int64, c_void_p, c_void_p], c_int),
     "ps_norm_leaky_bwd": ([c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_int64, c_int, c_void_p], c_int),
     "ps_l2norm_rows": ([c_void_p, c_int64, c_int64, c_int, c_void_p, c_void_p], c_int),
     "ps_leaky_bwd": ([c_void_p, c_void_p, c_int64, c_void_p], c_int),
@@ -256,18 +256,30 @@ def _aggregate_fwd(hin, self_rows, din, z, nbz, nbw, dh, cat, inv_wsum, n, T):
                                  _p(inv_wsum, torch.float32), _stream()))
 
 
-def aggregate_bwd(dcat, col_off, dh, seg_off, pair_q, nbw, inv_wsum, T, z, tag="aggregate_bwd"):
+AGG_BWD_CHUNK = 64  # pairs per warp-sized work unit of the aggregation backward
+
+
+def aggregate_bwd_chunks(seg_off, chunk_pairs=AGG_BWD_CHUNK):
+    """chunk_off int32 [nz+1] for ps_aggregate_bwd (index arithmetic on the device, no sync)."""
+    n_chunks = (seg_off[1:] - seg_off[:-1] + (chunk_pairs - 1)) // chunk_pairs
+    chunk_off = torch.zeros_like(seg_off)
+    chunk_off[1:] = torch.cumsum(n_chunks, 0)
+    return chunk_off
+
+
+def aggregate_bwd(dcat, col_off, dh, seg_off, pair_q, nbw, inv_wsum, T, z, chunk_off=None, chunk_pairs=AGG_BWD_CHUNK,
+                  tag="aggregate_bwd"):
     pairs, nz = pair_q.numel(), z.shape[0]
+    if chunk_off is None:
+        chunk_off = aggregate_bwd_chunks(seg_off, chunk_pairs)
+    max_chunks = pairs // chunk_pairs + nz  # upper bound of chunk_off[-1], known without a device read
+    ws = torch.empty((max(max_chunks, 1), dh), dtype=torch.float32, device=z.device)
     # algorithmic bytes: one dh-wide dcat row per (target, slot) pair + pair index/weight/inv_wsum, Z read + written
     with _Timed(tag, 2.0 * pairs * dh, float(pairs) * (dh * 4 + 12) + float(nz) * (2 * dh * 4 + 8)):
-        _aggregate_bwd(dcat, col_off, dh, seg_off, pair_q, nbw, inv_wsum, T, z)
-
-
-def _aggregate_bwd(dcat, col_off, dh, seg_off, pair_q, nbw, inv_wsum, T, z):
-    check(lib().ps_aggregate_bwd(_p(dcat, torch.float32), _ld(dcat), int(col_off), int(dh),
-                                 _p(seg_off, torch.int32), _p(pair_q, torch.int32), _p(nbw, torch.float32),
-                                 _p(inv_wsum, torch.float32), int(T), _p(z, torch.float32), _ld(z),
-                                 int(z.shape[0]), _stream()))
+        check(lib().ps_aggregate_bwd(_p(dcat, torch.float32), _ld(dcat), int(col_off), int(dh),
+                                     _p(seg_off, torch.int32), _p(chunk_off, torch.int32), int(chunk_pairs), int(max_chunks),
+                                     _p(pair_q, torch.int32), _p(nbw, torch.float32), _p(inv_wsum, torch.float32), int(T),
+                                     _p(z, torch.float32), _ld(z), int(nz), _p(ws, torch.float32), _stream()))
 
 
 def norm_leaky_bwd(h, norm, dh, dpre):

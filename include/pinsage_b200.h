@@ -92,14 +92,19 @@ int ps_gemm_backend(int mode);
 int ps_aggregate_fwd(const float* hin, int64_t ld_hin, const int32_t* self_rows, int din,
                      const float* z, int64_t ldz, const int32_t* nbz, const float* nbw, int T, int dh,
                      int64_t n, float* cat, int64_t ldcat, float* inv_wsum, ps_stream_t stream);
-/* ---- K11: backward of the aggregation as a segmented gather (no atomics).  For z-row u
- *      with incoming (target, slot) pairs pair_q[seg_off[u] .. seg_off[u+1]) (q = i*T + t):
+/* ---- K11: backward of the aggregation as a load-balanced segmented gather (no atomics,
+ *      deterministic).  For z-row u with incoming (target, slot) pairs
+ *      pair_q[seg_off[u] .. seg_off[u+1]) (q = i*T + t):
  *        z[u, :] = leaky'(z[u, :]) * sum_q nbw[q] * inv_wsum[q / T] * dcat[q / T, col_off : col_off+dh]
- *      (z holds leaky_relu outputs on entry and d(pre-activation) on exit). ---- */
+ *      (z holds leaky_relu outputs on entry and d(pre-activation) on exit; a row without
+ *      pairs gets zeros).  Segments are cut into chunks of at most chunk_pairs pairs, one
+ *      warp each: chunk_off[u] = sum_{v<u} ceil(len(v) / chunk_pairs), int32 [n_zrows+1];
+ *      max_chunks >= chunk_off[n_zrows] sizes the launch (no host sync needed) and
+ *      partial_ws holds max_chunks * dh floats of scratch for rows that span several chunks. ---- */
 int ps_aggregate_bwd(const float* dcat, int64_t ldcat, int col_off, int dh,
-                     const int32_t* seg_off, const int32_t* pair_q, const float* nbw,
-                     const float* inv_wsum, int T, float* z, int64_t ldz, int64_t n_zrows,
-                     ps_stream_t stream);
+                     const int32_t* seg_off, const int32_t* chunk_off, int chunk_pairs, int64_t max_chunks,
+                     const int32_t* pair_q, const float* nbw, const float* inv_wsum, int T,
+                     float* z, int64_t ldz, int64_t n_zrows, float* partial_ws, ps_stream_t stream);
 /* backward of  h = y / ||y||,  y = leaky_relu(pre)  (pinsage_model.py:209-210):
  *   dpre = leaky'(h) * (dh - h * (h . dh)) / norm */
 int ps_norm_leaky_bwd(const float* h, int64_t ldh, const float* norm, const float* dh, int64_t lddh,

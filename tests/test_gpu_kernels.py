@@ -139,6 +139,38 @@ def test_aggregate_fwd_bwd(nat, n, T, din, dh):
     assert rel(zz, want) < 1e-5
 
 
+def test_aggregate_bwd_skewed_segments(nat):
+    """Load-balanced backward: one z-row that owns thousands of pairs (split over many chunks), rows that own
+    none, and everything in between; the result must not depend on the chunk size."""
+    torch.manual_seed(9)
+    n, T, din, dh, nz = 4000, 20, 64, 256, 3000
+    z = leaky(torch.randn(nz, dh, device="cuda"))
+    hot = torch.rand(n, T, device="cuda") < 0.3
+    nbz = torch.where(hot, torch.zeros(n, T, device="cuda", dtype=torch.int64), torch.randint(1, nz // 2, (n, T), device="cuda")).to(torch.int32)
+    w = torch.randint(1, 40, (n, T), device="cuda").float() / 500
+    inv = (1 / w.sum(1)).contiguous()
+    dcat = torch.randn(n, din + dh, device="cuda")
+    flat = nbz.reshape(-1)
+    _, order = torch.sort(flat)
+    seg = torch.zeros(nz + 1, dtype=torch.int32, device="cuda")
+    seg[1:] = torch.cumsum(torch.bincount(flat, minlength=nz), 0)
+    coef = (w.double() * inv.double()[:, None]).reshape(-1)
+    want = torch.zeros(nz, dh, device="cuda", dtype=torch.float64).index_add_(
+        0, flat.long(), coef[:, None] * dcat[:, din:].double().repeat_interleave(T, 0))
+    want = want * torch.where(z > 0, 1.0, 0.01).double()
+    assert int(seg[1]) > 20000 and bool((want[nz // 2:] == 0).all())
+    outs = []
+    for chunk in (64, 7, 100000):
+        zz = z.clone()
+        nat.aggregate_bwd(dcat, din, dh, seg, order.to(torch.int32), w, inv, T, zz, chunk_pairs=chunk)
+        assert rel(zz, want) < 1e-5
+        assert bool((zz[nz // 2:] == 0).all())
+        outs.append(zz)
+    again = z.clone()
+    nat.aggregate_bwd(dcat, din, dh, seg, order.to(torch.int32), w, inv, T, again, chunk_pairs=64)
+    assert torch.equal(again, outs[0])  # deterministic (no atomics)
+
+
 def test_rowwise_kernels(nat):
     torch.manual_seed(3)
     n, d = 1234, 128
