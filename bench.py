@@ -256,9 +256,12 @@ def run_ours(args, wl):
     ps_dist.attach(trainer, rank, world)
     nbhds_cpu = trainer.nbhds
 
+    pending = [trainer.prefetch()]  # batch i+1 is sampled + planned on a side stream while step i runs
+
     def device_step():
-        batch, _ = pst.sample_batch(trainer.all_ids, positives, B, trainer.nbhds, hard_negatives=False)
-        return trainer.train_batch(batch)
+        out = trainer.train_batch(pending[0])
+        pending[0] = trainer.prefetch()
+        return out
 
     for _ in range(args.warmup):
         device_step()
@@ -295,10 +298,21 @@ def run_ours(args, wl):
     ids_cpu = torch.arange(N)
     pinned = torch.empty((B, 3), dtype=torch.int64).pin_memory()
 
+    pinned2 = torch.empty((B, 3), dtype=torch.int64).pin_memory()
+    bufs = [pinned, pinned2]
+    e2e_state = {"i": 0, "pending": None}
+
+    def e2e_prefetch():
+        buf = bufs[e2e_state["i"] & 1]; e2e_state["i"] += 1
+        batch, _ = pst.sample_batch(ids_cpu, pos_cpu, B, nbhds_cpu, hard_negatives=False)  # host sampling
+        buf.copy_(batch)
+        return trainer.prefetch(buf)  # H2D of the pinned batch + planning, on the side stream
+
     def e2e_step():
-        batch, _ = pst.sample_batch(ids_cpu, pos_cpu, B, nbhds_cpu, hard_negatives=False)
-        pinned.copy_(batch)
-        out = trainer.train_batch(pinned)
+        if e2e_state["pending"] is None:
+            e2e_state["pending"] = e2e_prefetch()
+        out = trainer.train_batch(e2e_state["pending"])
+        e2e_state["pending"] = e2e_prefetch()
         return float(out[0])  # D2H read of the step's result
 
     for _ in range(args.warmup):

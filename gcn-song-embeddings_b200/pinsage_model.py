@@ -118,7 +118,7 @@ def precompute_neighborhoods_topt(g, n_items, n_hops, alpha, T, path, seed=None)
     weights, nodes = out["weights"].cpu(), out["nodes"].cpu()
     # keep the engine-native device copy (int32 / float32) attached, so the trainer does not upload it again
     table = NeighborTable.__new__(NeighborTable)
-    table.nodes, table.w, table.n, table.Tp = out["nodes_i32"], out["weights_f32"], n_items, T
+    table.nodes, table.w, table.n, table.Tp, table.scratch = out["nodes_i32"], out["weights_f32"], n_items, T, {}
     weights._ps_table = table
     print(f"{n_items}/{n_items} done.\n{time.time() - t0}s elapsed.")
     if path is not None:

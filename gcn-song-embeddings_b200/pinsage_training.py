@@ -206,14 +206,29 @@ class PinSage():
             self._pos_src = self.positives
         return self._pos_dev
 
-    def train_batch(self, batch):
-        """One optimiser step on a batch of (q, pos, neg) triples (pinsage_training.py:181-214).
-        Returns (loss, node_feat_loss, variance) as 0-dim device tensors."""
+    def prefetch(self, batch=None):
+        """Start preparing the NEXT batch (frontier plans, backward transposes: index work that does not depend
+        on the weights) on a side stream while the current step's kernels run.  With batch=None a batch is drawn
+        on the device by sample_batch.  Returns a handle to pass to train_batch."""
+        sampler = None
+        if batch is None:
+            positives = self._positives_dev()
+            sampler = lambda: sample_batch(self.all_ids, positives, self.batch_size, self.nbhds,
+                                           hard_negatives=self.hard_negatives, hn_min=self.hn_min, hn_max=self.hn_max)[0]
+        else:
+            batch = torch.as_tensor(batch)
         if not self.reference_compat:
             self.model.T = self.T  # the reference never re-reads T after construction (grid_search.py:46-47)
-        batch = torch.as_tensor(batch).to("cuda", torch.int64, non_blocking=True)
+        return self.model.engine.prepare(batch, sampler)
+
+    def train_batch(self, batch):
+        """One optimiser step on a batch of (q, pos, neg) triples (pinsage_training.py:181-214).  `batch` is an
+        int64 [B,3] tensor (host or device) or a handle from prefetch().  Returns (loss, node_feat_loss,
+        variance) as 0-dim device tensors."""
+        prep = batch if hasattr(batch, "plan") else self.prefetch(batch)
+        batch = prep.batch
         feats = self._feats()
-        loss, emb, triples = self.model.engine.train_step(feats, batch, self.margin, self.reference_compat)
+        loss, emb, triples = self.model.engine.train_step(feats, prep, self.margin, self.reference_compat)
         if self._grad_sync is not None:
             self._grad_sync()
         self.optimizer.step()
@@ -231,7 +246,7 @@ class PinSage():
     def train(self):
         """Train the model (pinsage_training.py:216-256)."""
         print("\033[0;33mTraining PinSage...\033[0m")
-        positives = self._positives_dev()
+        nxt = self.prefetch()
         while self.e < self.epochs:
             print(f"Training epoch {self.e+1}/{self.epochs}...")
             cur_lr = self.optimizer.param_groups[0]["lr"]
@@ -239,9 +254,9 @@ class PinSage():
             pbar = tqdm(total=self.b_per_e)
             pbar.update(1)
             while self.b < self.b_per_e:
-                batch, _ = sample_batch(self.all_ids, positives, self.batch_size, self.nbhds,
-                                        hard_negatives=self.hard_negatives, hn_min=self.hn_min, hn_max=self.hn_max)
-                loss, node_feat_loss, variance = self.train_batch(batch)
+                cur = nxt
+                loss, node_feat_loss, variance = self.train_batch(cur)  # launches this step's kernels ...
+                nxt = self.prefetch()                                    # ... and prepares the next batch meanwhile
                 pbar.update(1)
                 if self.b % 50 == 0:  # reading the loss synchronises the device: not every step
                     pbar.set_description(f"Loss = {float(loss)}, bathes done")

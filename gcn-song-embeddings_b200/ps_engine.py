@@ -46,6 +46,7 @@ class NeighborTable:
         self.nodes = _dev(nodes, torch.int32, device).contiguous()
         self.w = _dev(weights, None, device).to(torch.float32).contiguous()
         self.n, self.Tp = self.nodes.shape
+        self.scratch = {}
 
     @classmethod
     def of(cls, nbhds) -> "NeighborTable":
@@ -82,6 +83,26 @@ class Plan:
     layers: List[LayerPlan] = field(default_factory=list)
 
 
+def _unique_inverse(ids: torch.Tensor, n_ids: int, scratch: dict):
+    """Sorted distinct values of `ids` (all in [0, n_ids)) and the position of every element among them.
+    Same result as torch.unique(ids, return_inverse=True) but through a dense flag/prefix-sum map over the id
+    space instead of a radix sort of the (much longer) id list."""
+    if ids.numel() < 65536 or n_ids > 64 * ids.numel():
+        uniq, inv = torch.unique(ids, return_inverse=True)
+        return uniq.to(torch.int64), inv
+    key = ("flag", torch.cuda.current_stream().cuda_stream if ids.is_cuda else 0)  # one scratch map per stream
+    flag = scratch.get(key)
+    if flag is None or flag.numel() != n_ids or flag.device != ids.device:
+        flag = scratch[key] = torch.empty(n_ids, dtype=torch.int32, device=ids.device)
+    flag.zero_()
+    idx = ids.to(torch.int64)
+    flag[idx] = 1
+    pos = torch.cumsum(flag, 0, dtype=torch.int32)
+    uniq = flag.nonzero().squeeze(1)
+    inv = (pos[idx] - 1).to(torch.int64)
+    return uniq, inv
+
+
 def build_plan(top: torch.Tensor, n_layers: int, T: int, table: NeighborTable, need_backward: bool) -> Plan:
     """T-hop computation graph around the distinct nodes `top` (sorted int64, on device).
     Restates relevant_nodes_per_layer_precomp (pinsage_model.py:156-168): layer l-1's
@@ -98,12 +119,12 @@ def build_plan(top: torch.Tensor, n_layers: int, T: int, table: NeighborTable, n
         w = table.w[cur, :T].contiguous()
         if l > 0:
             allv = torch.cat([nb.reshape(-1).to(torch.int64), cur])
-            nxt, inv = torch.unique(allv, return_inverse=True)
+            nxt, inv = _unique_inverse(allv, table.n, table.scratch)
             nbz = inv[: n * T].view(n, T).to(torch.int32).contiguous()
             self_rows = inv[n * T:].to(torch.int32).contiguous()
             zrows, nz = None, nxt.numel()
         else:
-            zr, inv = torch.unique(nb.reshape(-1), return_inverse=True)
+            zr, inv = _unique_inverse(nb.reshape(-1), table.n, table.scratch)
             nbz = inv.view(n, T).to(torch.int32).contiguous()
             self_rows = cur.to(torch.int32).contiguous()
             zrows, nz, nxt = zr.to(torch.int32).contiguous(), zr.numel(), None
@@ -119,6 +140,22 @@ def build_plan(top: torch.Tensor, n_layers: int, T: int, table: NeighborTable, n
         plan.layers[l] = lp
         cur = nxt
     return plan
+
+
+@dataclass
+class Prepared:
+    """A training batch with everything index-only already built (Engine.prepare)."""
+    batch: torch.Tensor      # int64 [B,3] on device
+    triples: torch.Tensor    # int32 [B,3] rows of the distinct-node embedding matrix
+    plan: Plan
+    counts: torch.Tensor     # int32 [3,U] occurrences of every distinct node per column
+    ready: object            # CUDA event recorded on the side stream
+
+    def tensors(self):
+        out = [self.batch, self.triples, self.counts, self.plan.top]
+        for lp in self.plan.layers:
+            out += [t for t in (lp.self_rows, lp.nbz, lp.w, lp.zrows, lp.seg_off, lp.pair_q, lp.chunk_off) if t is not None]
+        return out
 
 
 def _splits_for(M, N, K):
@@ -251,27 +288,49 @@ class Engine:
         return grads
 
     # ---- fused training step -----------------------------------------------------------
-    def train_step(self, feats: torch.Tensor, batch: torch.Tensor, margin: float, reference_compat: bool = True):
-        """Forward of the distinct nodes of `batch` (int64 [B,3] on device), max-margin loss,
-        backward into the parameters' .grad.  Returns (loss [1] device tensor, h_q [B, out])."""
+    def prepare(self, batch, sampler=None) -> "Prepared":
+        """Index-only preparation of a training batch on a high-priority side stream, so it overlaps the
+        previous step's kernels: the distinct nodes of the batch, the layer plans, the backward transposes and
+        the duplicate counts.  None of it depends on the model weights.  `batch` is an int64 [B,3] tensor (host
+        tensors are copied on the side stream; device tensors make the side stream wait for the current one) or
+        None with `sampler` a callable that draws the batch on the side stream."""
         m = self.model
-        B = batch.shape[0]
-        top, inv = torch.unique(batch.reshape(-1), return_inverse=True)
-        triples = inv.view(B, 3).to(torch.int32).contiguous()
-        table = NeighborTable.of(m.nbhds)
-        plan = build_plan(top, m.n_layers, m.T, table, need_backward=True)
-        out, ctx = self.forward(feats, plan, keep=True)
-        U = top.numel()
-        counts = None
-        if reference_compat:
-            counts = torch.empty((3, U), dtype=torch.int32, device="cuda")
-            nat.count_triples(triples, U, counts)
+        main = torch.cuda.current_stream()
+        if getattr(self, "plan_stream", None) is None:
+            self.plan_stream = torch.cuda.Stream(priority=-1)
+        side = self.plan_stream
+        if batch is not None and batch.is_cuda:
+            side.wait_stream(main)
+        with torch.cuda.stream(side):
+            if batch is None:
+                batch = sampler()
+            batch = batch.to("cuda", torch.int64, non_blocking=True)
+            B = batch.shape[0]
+            top, inv = torch.unique(batch.reshape(-1), return_inverse=True)
+            triples = inv.view(B, 3).to(torch.int32).contiguous()
+            plan = build_plan(top, m.n_layers, m.T, NeighborTable.of(m.nbhds), need_backward=True)
+            counts = torch.empty((3, top.numel()), dtype=torch.int32, device="cuda")
+            nat.count_triples(triples, top.numel(), counts)
+            ready = torch.cuda.Event()
+            ready.record(side)
+        return Prepared(batch=batch, triples=triples, plan=plan, counts=counts, ready=ready)
+
+    def train_step(self, feats: torch.Tensor, batch, margin: float, reference_compat: bool = True):
+        """Forward of the distinct nodes of a batch, max-margin loss, backward into the parameters' .grad.
+        `batch` is an int64 [B,3] tensor or a Prepared from prepare().  Returns (loss [1], embeddings of the
+        distinct nodes [U, out], triples int32 [B,3] indexing them), all on the device."""
+        prep = batch if isinstance(batch, Prepared) else self.prepare(batch)
+        main = torch.cuda.current_stream()
+        main.wait_event(prep.ready)
+        for t in prep.tensors():
+            t.record_stream(main)  # allocated on the side stream, consumed here
+        out, ctx = self.forward(feats, prep.plan, keep=True)
         loss = torch.zeros(1, dtype=torch.float32, device="cuda")
         d_out = torch.zeros_like(out)
-        nat.margin_loss_fwd_bwd(out, triples, margin, 1.0, counts, loss, d_out)
+        nat.margin_loss_fwd_bwd(out, prep.triples, margin, 1.0, prep.counts if reference_compat else None, loss, d_out)
         grads = self.zero_grads()
         self.backward(ctx, d_out, grads)
-        return loss, out, triples
+        return loss, out, prep.triples
 
     @torch.no_grad()
     def embed(self, feats: torch.Tensor, nodes: torch.Tensor) -> torch.Tensor:

@@ -99,6 +99,18 @@ def test_build_plan_matches_reference_frontier(golden, tag, L, T):
         ps_engine.build_plan(top, L, 999, tab, False)
 
 
+def test_unique_inverse_dense_map_equals_torch_unique():
+    import ps_engine
+    torch.manual_seed(3)
+    ids = torch.randint(0, 50_000, (200_000,), dtype=torch.int32)
+    u, inv = ps_engine._unique_inverse(ids, 50_000, {})
+    tu, tinv = torch.unique(ids, return_inverse=True)
+    assert torch.equal(u, tu.to(torch.int64)) and torch.equal(inv, tinv)
+    small = torch.randint(0, 50_000, (100,))
+    u, inv = ps_engine._unique_inverse(small, 50_000, {})
+    assert torch.equal(u[inv], small)
+
+
 @pytest.mark.parametrize("n,P,B", [(500, 2000, 64), (200_000, 3_000_000, 512)])
 def test_batch_sampling_properties(n, P, B):
     """Same guarantees as the reference's sample_batch with easy negatives: distinct rows of
