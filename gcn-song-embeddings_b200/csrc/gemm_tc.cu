@@ -209,6 +209,29 @@ struct Operand {
             }
         }
     }
+    // L2 prefetch of the elements this thread will load for the k-block at k0 (no registers held; the later
+    // LDG then pays an L2 hit instead of an HBM round trip).  Gathered MN-major rows are skipped (their
+    // address needs the index first).
+    __device__ __forceinline__ void prefetch(int64_t k0, int64_t K) const {
+        if (KMAJOR) {
+            if (k0 + kq < K && (kq == 0 || kq == 28)) {  // the two ends of the 128-byte row segment cover its cache line(s)
+#pragma unroll
+                for (int j = 0; j < NJ; ++j) {
+                    const float* p = PRECOMP ? base[j] + k0
+                                             : base[0] + static_cast<int64_t>(min(row0 + 32 * j, ext - 1)) * ld + k0;
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+                }
+            }
+        } else if (rows == nullptr) {
+            if ((threadIdx.x & 7) == 0) {  // one thread per 128 bytes of a k-row
+#pragma unroll
+                for (int j = 0; j < NJ; ++j) {
+                    const int64_t k = k0 + kq + RPP * j;
+                    if (k < K) asm volatile("prefetch.global.L2 [%0];" ::"l"(base[0] + k * ld));
+                }
+            }
+        }
+    }
     template <int J0, int CNT>
     __device__ __forceinline__ void store(uint8_t* hi, uint8_t* lo, const float4 (&v)[CNT]) const {
 #pragma unroll
@@ -320,6 +343,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(TcArgs a) {
             opb.init(a.Q, a.ldq, a.q_rows, wk.n0, a.N, t);
             for (int kb = 0; kb < wk.num_kb; ++kb) {
                 const int64_t k0 = static_cast<int64_t>(wk.kb_begin + kb) * BK;
+                if (kb + 1 < wk.num_kb) { opa.prefetch(k0 + BK, a.K); opb.prefetch(k0 + BK, a.K); }
                 float4 va[OpA::NJ];
                 opa.template load<0, OpA::NJ>(va, k0, a.K);  // issued before the stage is free: the loads overlap the wait
                 float4 vb[HB];
