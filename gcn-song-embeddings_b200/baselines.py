@@ -1,0 +1,92 @@
+"""PinSage-side slice of the reference's `baselines` module (reference:
+/root/reference/baselines.py:33-103, 281-377): the recommender ABCs, cosine kNN from
+embeddings (on the device, ps_knn), the per-track embedding loader and the PinSage wrapper.
+The competing recommenders (PPR / Jaccard / node2vec / implicit CF / GraphSAGE) are out of
+scope."""
+from __future__ import annotations
+
+import os
+import time
+from abc import ABC, abstractmethod
+
+import torch
+from tqdm import tqdm
+
+from pinsage_training import PinSage
+from ps_knn import cosine_sim_ab, knn_from_emb  # noqa: F401  (re-exported reference names)
+
+
+class PredictionModel(ABC):
+    """Base recommender class (baselines.py:33-46)."""
+
+    @abstractmethod
+    def __init__(self):
+        pass
+
+    @abstractmethod
+    def train(self, g, ids, train_set, test_set, features):
+        pass
+
+    @abstractmethod
+    def knn(self, nodeset, k):
+        pass
+
+
+class EmbeddingModel(PredictionModel):
+    """An embedding-based recommender (baselines.py:48-53)."""
+
+    @abstractmethod
+    def embed(self, nodeset):
+        pass
+
+
+def _load_embeddings(ids, load_dir):
+    """Stack the per-track `<id>.pt` vectors (baselines.py:281-294)."""
+    emb_list = [torch.load(os.path.join(load_dir, track_id + ".pt")) for track_id in tqdm(ids, desc="Loading embeddings")]
+    return torch.stack(emb_list, dim=0)
+
+
+class EmbLoader(EmbeddingModel):
+    """Load precomputed embeddings as a recommender method (baselines.py:297-328)."""
+
+    def __init__(self, load_dir):
+        self.load_dir = load_dir
+        self.embedding = None
+
+    def train(self, g, ids, train_set, test_set, features):
+        print(f"Loading embeddings from {self.load_dir} ...")
+        self.embedding = _load_embeddings(ids, self.load_dir)
+
+    def embed(self, nodeset):
+        return self.embedding[nodeset, :]
+
+    def knn(self, nodeset, k):
+        return knn_from_emb(self.embedding, nodeset, k)
+
+
+class PinSageWrapper(EmbeddingModel):
+    """Train PinSage behind the baseline interface (baselines.py:331-377).  train_params are
+    applied as attributes after construction, as the reference does."""
+
+    def __init__(self, train_params=None, run_name=None, log=True):
+        self.embedding = None
+        self.train_params = train_params if train_params else {}
+        self.run_name = run_name if run_name else time.strftime("%X %x")
+        self.log = log
+
+    def train(self, g, ids, train_set, test_set, features):
+        print("Training PinSage with parameters:")
+        print(self.train_params)
+        self.trainer = PinSage(g, len(ids), features, train_set, log=self.log, load_save=False)
+        for param, value in self.train_params.items():
+            setattr(self.trainer, param, value)
+        self.trainer.run_name = self.run_name
+        self.trainer.train()
+        print("Embedding...")
+        self.embedding = self.trainer.embed(torch.arange(len(ids)), bsize=None)
+
+    def embed(self, nodeset):
+        return self.embedding[nodeset, :]
+
+    def knn(self, nodeset, k):
+        return knn_from_emb(self.embedding, nodeset, k)

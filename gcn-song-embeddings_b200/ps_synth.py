@@ -76,3 +76,34 @@ def cooccurrence_positives(indptr, indices, n_tracks, n_pairs, seed=2):
     b = indices[indptr[c] + r].to(torch.int64)
     keep = a != b
     return torch.stack([a[keep], b[keep]], 1)
+
+
+def write_dataset(out_dir, n_tracks, n_cols, n_edges, feat_dim, n_pos, seed=0, features_name="features_openl3",
+                  positives_name="positives_lfm.json"):
+    """Write a synthetic dataset in the reference's on-disk schema (tracks.json, collections.json, graph.json
+    with both edge directions, one <track_id>.pt feature vector per track, positives json); see
+    spotify_graph.py for the schema.  Small sizes only (JSON + one file per track)."""
+    import json
+    import os
+    indptr, indices, _ = bipartite_csr(n_tracks, n_cols, n_edges, seed=seed)
+    track_ids = [f"t{i:06d}" for i in range(n_tracks)]
+    col_ids = [f"c{i:06d}" for i in range(n_cols)]
+    all_ids = track_ids + col_ids
+    deg = (indptr[1:] - indptr[:-1])
+    src = torch.repeat_interleave(torch.arange(n_tracks + n_cols), deg)
+    edges = [{"from": all_ids[a], "to": all_ids[b]} for a, b in zip(src.tolist(), indices.tolist())]
+    os.makedirs(os.path.join(out_dir, features_name), exist_ok=True)
+    with open(os.path.join(out_dir, "tracks.json"), "w") as f:
+        json.dump({t: {"name": f"song {i}", "artist": f"artist {i % 7}"} for i, t in enumerate(track_ids)}, f)
+    with open(os.path.join(out_dir, "collections.json"), "w") as f:
+        json.dump({c: {"name": f"playlist {i}"} for i, c in enumerate(col_ids)}, f)
+    with open(os.path.join(out_dir, "graph.json"), "w") as f:
+        json.dump({"tracks": track_ids, "collections": col_ids, "edges": edges}, f)
+    gen = torch.Generator().manual_seed(seed + 1)
+    raw = torch.randn((n_tracks, feat_dim), generator=gen) * 2.0 + 0.5
+    for i, t in enumerate(track_ids):
+        torch.save(raw[i].clone(), os.path.join(out_dir, features_name, t + ".pt"))
+    pos = cooccurrence_positives(indptr, indices, n_tracks, n_pos, seed=seed + 2)
+    with open(os.path.join(out_dir, positives_name), "w") as f:
+        json.dump([{"a": track_ids[a], "b": track_ids[b]} for a, b in pos.tolist()], f)
+    return out_dir

@@ -19,6 +19,7 @@ ROOT = os.path.dirname(HERE)
 sys.path.insert(0, os.path.join(HERE, "refshim"))
 sys.path.insert(1, "/root/reference")
 sys.path.insert(2, ROOT)
+sys.path.insert(3, os.path.join(ROOT, "gcn-song-embeddings_b200"))  # AFTER the reference: only ps_synth comes from here
 
 import dgl  # noqa: E402  (the shim)
 import pinsage_model as ref_psm  # noqa: E402  (the reference)
@@ -243,8 +244,33 @@ def gen_metrics_knn():
     print("metrics", out["toy_hr"], out["toy_mrr"])
 
 
+def gen_dataset():
+    """The reference's own loader (SpotifyGraph, spotify_graph.py:15-110) on a tiny synthetic dataset written in
+    its on-disk schema; the dataset content is stored with the outputs so the test can rewrite the files."""
+    import json
+    import ps_synth
+    from spotify_graph import SpotifyGraph as RefSpotifyGraph  # the reference
+    with tempfile.TemporaryDirectory() as tmp:
+        ps_synth.write_dataset(tmp, 60, 12, 400, 8, 300, seed=5)
+        ds = RefSpotifyGraph(tmp, os.path.join(tmp, "features_openl3"))
+        g, track_ids, col_ids, features = ds.to_dgl_graph()
+        pos = ds.load_positives(os.path.join(tmp, "positives_lfm.json"))
+        train, test = ds.load_positives_split(os.path.join(tmp, "positives_lfm.json"))
+        indptr, indices = g.csr()
+        graph_json = json.load(open(os.path.join(tmp, "graph.json")))
+        raw = torch.stack([torch.load(os.path.join(tmp, "features_openl3", t + ".pt")) for t in track_ids])
+        pos_json = json.load(open(os.path.join(tmp, "positives_lfm.json")))
+    out = {"track_ids": np.array(track_ids), "col_ids": np.array(col_ids),
+           "edges_from": np.array([e["from"] for e in graph_json["edges"]]), "edges_to": np.array([e["to"] for e in graph_json["edges"]]),
+           "raw_features": raw.numpy(), "pos_a": np.array([p["a"] for p in pos_json]), "pos_b": np.array([p["b"] for p in pos_json]),
+           "indptr": indptr, "indices": indices, "features": features.numpy(), "positives": pos.numpy(),
+           "train": train.numpy(), "test": test.numpy(), "nbhds_path_tail": np.array(os.path.basename(g.nbhds_path))}
+    np.savez_compressed(os.path.join(OUT, "dataset.npz"), **out)
+    print("dataset", features.shape, pos.shape, train.shape, test.shape)
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["walk_topt", "walk_dist", "frontier", "model", "train_steps", "loss", "metrics_knn"]
+    which = sys.argv[1:] or ["walk_topt", "walk_dist", "frontier", "model", "train_steps", "loss", "metrics_knn", "dataset"]
     if "walk_topt" in which: gen_walk_topt()
     if "walk_dist" in which: gen_walk_dist()
     if "frontier" in which: gen_frontier()
@@ -255,3 +281,4 @@ if __name__ == "__main__":
     if "train_steps" in which: gen_train_steps()
     if "loss" in which: gen_loss()
     if "metrics_knn" in which: gen_metrics_knn()
+    if "dataset" in which: gen_dataset()

@@ -173,3 +173,50 @@ def test_metrics_match_oracle(golden):
     for K, hr, m in zip(g["toy_K"], g["toy_hr"], g["toy_mrr"]):
         assert ps_eval.hit_rate(torch.from_numpy(g["toy_knn"]), torch.from_numpy(g["toy_pos"]), int(K)) == pytest.approx(hr)
         assert ps_eval.mrr(torch.from_numpy(g["toy_knn"]), torch.from_numpy(g["toy_pos"]), int(K)) == pytest.approx(m)
+
+
+def _rewrite_dataset(g, d):
+    """Recreate the dataset files of tests/golden/dataset.npz (the content the reference's loader was run on)."""
+    import json
+    os.makedirs(os.path.join(d, "features_openl3"), exist_ok=True)
+    json.dump({t: {"name": t, "artist": "a"} for t in g["track_ids"].tolist()}, open(os.path.join(d, "tracks.json"), "w"))
+    json.dump({c: {} for c in g["col_ids"].tolist()}, open(os.path.join(d, "collections.json"), "w"))
+    json.dump({"tracks": g["track_ids"].tolist(), "collections": g["col_ids"].tolist(),
+               "edges": [{"from": a, "to": b} for a, b in zip(g["edges_from"].tolist(), g["edges_to"].tolist())]},
+              open(os.path.join(d, "graph.json"), "w"))
+    for t, row in zip(g["track_ids"].tolist(), g["raw_features"]):
+        torch.save(torch.from_numpy(row.copy()), os.path.join(d, "features_openl3", t + ".pt"))
+    json.dump([{"a": a, "b": b} for a, b in zip(g["pos_a"].tolist(), g["pos_b"].tolist())], open(os.path.join(d, "positives_lfm.json"), "w"))
+
+
+def test_spotify_graph_matches_reference_loader(golden, tmp_path):
+    """Drop-in SpotifyGraph == the reference's loader on the same files: node numbering, adjacency (order of
+    successors included), standardised features, positives and the 70/30 split."""
+    from spotify_graph import SpotifyGraph
+    g = golden("dataset")
+    d = str(tmp_path)
+    _rewrite_dataset(g, d)
+    ds = SpotifyGraph(d, os.path.join(d, "features_openl3"))
+    graph, track_ids, col_ids, features = ds.to_dgl_graph()
+    assert track_ids == g["track_ids"].tolist() and col_ids == g["col_ids"].tolist()
+    assert np.array_equal(graph.indptr.numpy(), g["indptr"]) and np.array_equal(graph.indices.numpy(), g["indices"])
+    assert os.path.basename(graph.nbhds_path) == str(g["nbhds_path_tail"]) and graph.base_dir == d
+    assert np.allclose(features.numpy(), g["features"], rtol=1e-6, atol=1e-7)
+    pos = ds.load_positives(os.path.join(d, "positives_lfm.json"))
+    assert np.array_equal(pos.numpy(), g["positives"])
+    train, test = ds.load_positives_split(os.path.join(d, "positives_lfm.json"))
+    assert np.array_equal(train.numpy(), g["train"]) and np.array_equal(test.numpy(), g["test"])
+
+
+def test_results_table_host_logic():
+    import eval as ev
+    from ps_graph import PSGraph
+    knn = torch.tensor([[1, 2, 3], [0, 2, 3], [3, 1, 0], [2, 0, 1]])
+    test_pos = torch.tensor([[0, 2], [1, 3], [2, 0], [3, 3]])
+    g = PSGraph.from_edges([0, 4, 1, 4, 2, 4, 3, 5, 0, 5], [4, 0, 4, 1, 4, 2, 5, 3, 5, 0], 4, 2)
+    kd = ev.KnnDict(); kd["m"] = (None, knn); kd.times["m"] = (1.0, 2.0, 3.0)
+    table = ev.compute_results_table(kd, test_pos, g, degree_thr=1)
+    assert table.loc["m", "hr (k=10)"] == pytest.approx(0.75)
+    assert table.loc["m", "mrr"] == pytest.approx((1 / 2 + 1 / 3 + 1 / 3 + 1 / 1000) / 4)
+    assert table.loc["m", "low-degree accuracy"] == pytest.approx((1 / 3 + 1 / 3 + 1 / 1000) / 3)  # node 0 has degree 2
+    assert table.loc["m", "t (knn)"] == 3.0
