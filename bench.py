@@ -258,9 +258,14 @@ def run_ours(args, wl):
 
     pending = [trainer.prefetch()]  # batch i+1 is sampled + planned on a side stream while step i runs
 
+    host = {"train": 0.0, "prefetch": 0.0}
+
     def device_step():
+        h0 = time.perf_counter()
         out = trainer.train_batch(pending[0])
+        h1 = time.perf_counter()
         pending[0] = trainer.prefetch()
+        host["train"] += h1 - h0; host["prefetch"] += time.perf_counter() - h1
         return out
 
     for _ in range(args.warmup):
@@ -274,6 +279,7 @@ def run_ours(args, wl):
     t0 = torch.cuda.Event(enable_timing=True); t1 = torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize(); ps_dist.barrier()
     w0 = time.perf_counter()
+    host["train"] = host["prefetch"] = 0.0
     t0.record()
     for _ in range(args.steps):
         torch.cuda.nvtx.range_push("ps_step")  # lets `ncu --nvtx --nvtx-include "ps_step/"` isolate the timed steps
@@ -284,6 +290,7 @@ def run_ours(args, wl):
     wall = time.perf_counter() - w0
     dev_ms = t0.elapsed_time(t1)
     launches = ps_native.launch_count - launches0
+    host_ms = {k: round(v * 1e3 / args.steps, 3) for k, v in host.items()}
     clocks = sampler.stop() if sampler else None
     prof = ps_native.profiler.summary(); ps_native.profiler = None
     step_ms = ps_dist.max_over_ranks(max(dev_ms, 0.0) / args.steps)
@@ -325,14 +332,16 @@ def run_ours(args, wl):
     e2e_ms = ps_dist.max_over_ranks((time.perf_counter() - w0) * 1e3 / args.steps)
     e2e_value = 3 * B * world / (e2e_ms * 1e-3)
 
-    if args.torch_profile and rank == 0:  # optional: where the non-kernel time of a step goes (not a bench number)
+    if args.torch_profile:  # optional: where the non-kernel time of a step goes (not a bench number); every rank steps
         from torch.profiler import ProfilerActivity, profile
         with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA]) as tp:
             for _ in range(3):
                 device_step()
             torch.cuda.synchronize()
-        with open(args.torch_profile, "w") as f:
-            f.write(tp.key_averages().table(sort_by="cuda_time_total", row_limit=60, max_name_column_width=70))
+        if rank == 0:
+            with open(args.torch_profile, "w") as f:
+                f.write(tp.key_averages().table(sort_by="cuda_time_total", row_limit=60, max_name_column_width=70))
+            tp.export_chrome_trace(args.torch_profile + ".trace.json")
 
     line = {"metric": METRIC, "value": round(value, 1), "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": round(step_ms, 3), "wall_ms_per_step": round(wall_ms, 3),
@@ -345,7 +354,7 @@ def run_ours(args, wl):
                      "sources": N, "n_hops": 500, "alpha": 0.85, "T": 100, "ms": round(walk_ms, 3),
                      "algorithmic_gbs": round(walk_steps_per_s * 28 / 1e9, 2),
                      "frac_of_hbm": round(walk_steps_per_s * 28 / 1e9 / peaks["hbm_gbs"], 4)},
-            "final_loss": final_loss}
+            "final_loss": final_loss, "host_ms_per_step": host_ms}
     if rank == 0:
         line["roofline"] = roofline_from_profile(prof, args.steps, peaks)
         if world == 1 and not args.no_cpu_baseline:

@@ -112,8 +112,32 @@ def sample_hard_negatives(all_ids, pos_batch, nbhds, min_rank, max_rank, referen
     return batch, nodeset
 
 
+_sampler_state = {"seed": None, "step": 0}
+
+
+def sample_batch_device(all_ids, positives, batch_size):
+    """Easy-negative batch int64 [B,3] drawn by ONE kernel (ps_sample_batch) with no host round trip: same law as
+    sample_positives_with_rep + sample_easy_negatives.  The Philox key is derived once from torch's seed
+    (torch.manual_seed controls it), the counter advances per call.  None if the sizes are outside the kernel's
+    limits (the torch path below handles those)."""
+    if os.environ.get("PS_NATIVE_SAMPLER", "1") == "0":
+        return None
+    if not (positives.is_cuda and all_ids.is_cuda and positives.dtype == torch.int64 and positives.is_contiguous()
+            and ps_native.sample_batch_supported(positives.shape[0], all_ids.shape[0], batch_size)):
+        return None
+    st = _sampler_state
+    if st["seed"] != torch.initial_seed():
+        st["seed"], st["step"] = torch.initial_seed(), 0
+    st["step"] += 1
+    return ps_native.sample_batch(positives, all_ids, all_ids.shape[0], batch_size, st["seed"], st["step"])
+
+
 def sample_batch(all_ids, positives, batch_size, nbhds, hard_negatives=True, hn_min=10, hn_max=100):
     """(batch int64 [B,3], nodeset) (pinsage_training.py:89-97)."""
+    if not hard_negatives:
+        batch = sample_batch_device(all_ids, positives, batch_size)
+        if batch is not None:
+            return batch, batch.flatten().unique()
     pos_batch = sample_positives_with_rep(positives, batch_size)
     if hard_negatives:
         return sample_hard_negatives(all_ids, pos_batch, nbhds, hn_min, hn_max)
@@ -213,8 +237,13 @@ class PinSage():
         sampler = None
         if batch is None:
             positives = self._positives_dev()
-            sampler = lambda: sample_batch(self.all_ids, positives, self.batch_size, self.nbhds,
-                                           hard_negatives=self.hard_negatives, hn_min=self.hn_min, hn_max=self.hn_max)[0]
+            def sampler():
+                if not self.hard_negatives:
+                    b = sample_batch_device(self.all_ids, positives, self.batch_size)  # one launch, no host sync
+                    if b is not None:
+                        return b
+                return sample_batch(self.all_ids, positives, self.batch_size, self.nbhds,
+                                    hard_negatives=self.hard_negatives, hn_min=self.hn_min, hn_max=self.hn_max)[0]
         else:
             batch = torch.as_tensor(batch)
         if not self.reference_compat:

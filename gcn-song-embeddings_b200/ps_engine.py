@@ -103,14 +103,16 @@ def _unique_inverse(ids: torch.Tensor, n_ids: int, scratch: dict):
     return uniq, inv
 
 
-def build_plan(top: torch.Tensor, n_layers: int, T: int, table: NeighborTable, need_backward: bool) -> Plan:
+def build_plan(top: torch.Tensor, n_layers: int, T: int, table: NeighborTable, need_backward: bool, check_ids: bool = True) -> Plan:
     """T-hop computation graph around the distinct nodes `top` (sorted int64, on device).
     Restates relevant_nodes_per_layer_precomp (pinsage_model.py:156-168): layer l-1's
     targets are unique(neighbours of layer l's targets + the targets themselves)."""
     if T > table.Tp:
         raise ValueError(f"T={T} exceeds the precomputed neighbourhood width {table.Tp}")
-    if top.numel() and (int(top.max()) >= table.n or int(top.min()) < 0):
-        raise IndexError("node id out of range")  # the reference raises IndexError on OOB ids too
+    if check_ids and top.numel():
+        lo, hi = top[[0, -1]].tolist()  # top is sorted: one host read
+        if hi >= table.n or lo < 0:
+            raise IndexError("node id out of range")  # the reference raises IndexError on OOB ids too
     plan = Plan(top=top, layers=[None] * n_layers)
     cur = top
     for l in reversed(range(n_layers)):
@@ -131,12 +133,11 @@ def build_plan(top: torch.Tensor, n_layers: int, T: int, table: NeighborTable, n
         lp = LayerPlan(n=n, nz=nz, self_rows=self_rows, nbz=nbz, w=w, zrows=zrows)
         if need_backward:
             flat = nbz.reshape(-1)
-            _, order = torch.sort(flat)
+            skeys, order = torch.sort(flat)
             lp.pair_q = order.to(torch.int32).contiguous()
-            seg = torch.zeros(nz + 1, dtype=torch.int32, device=flat.device)
-            seg[1:] = torch.cumsum(torch.bincount(flat, minlength=nz), 0)
-            lp.seg_off = seg
-            lp.chunk_off = nat.aggregate_bwd_chunks(seg)
+            # segment starts of the sorted keys (no bincount: it reads its maximum back to the host)
+            lp.seg_off = torch.searchsorted(skeys, torch.arange(nz + 1, dtype=torch.int32, device=flat.device)).to(torch.int32)
+            lp.chunk_off = nat.aggregate_bwd_chunks(lp.seg_off)
         plan.layers[l] = lp
         cur = nxt
     return plan
@@ -301,6 +302,13 @@ class Engine:
         side = self.plan_stream
         if batch is not None and batch.is_cuda:
             side.wait_stream(main)
+        check_ids = True
+        if batch is None:
+            check_ids = False  # drawn from `positives` / `all_ids` below: in range by construction
+        elif not batch.is_cuda:
+            if batch.numel() and (int(batch.max()) >= NeighborTable.of(m.nbhds).n or int(batch.min()) < 0):
+                raise IndexError("node id out of range")
+            check_ids = False  # checked on the host copy, no device read needed
         with torch.cuda.stream(side):
             if batch is None:
                 batch = sampler()
@@ -308,7 +316,7 @@ class Engine:
             B = batch.shape[0]
             top, inv = torch.unique(batch.reshape(-1), return_inverse=True)
             triples = inv.view(B, 3).to(torch.int32).contiguous()
-            plan = build_plan(top, m.n_layers, m.T, NeighborTable.of(m.nbhds), need_backward=True)
+            plan = build_plan(top, m.n_layers, m.T, NeighborTable.of(m.nbhds), need_backward=True, check_ids=check_ids)
             counts = torch.empty((3, top.numel()), dtype=torch.int32, device="cuda")
             nat.count_triples(triples, top.numel(), counts)
             ready = torch.cuda.Event()

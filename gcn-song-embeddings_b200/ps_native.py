@@ -8,6 +8,7 @@ from __future__ import annotations
 
 import ctypes
 import os
+import threading
 from ctypes import c_char_p, c_double, c_float, c_int, c_int64, c_uint64, c_void_p
 
 import torch
@@ -16,7 +17,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libpinsage_b200.so")
 
 _lib = None
-_device_set = None
+_tls = threading.local()  # the library's CUDA runtime keeps a current device per host thread
 
 
 class NativeError(RuntimeError):
@@ -47,6 +48,9 @@ _SIGNATURES = {
     "ps_count_triples": ([c_void_p, c_int64, c_int64, c_void_p, c_void_p], c_int),
     "ps_margin_loss_fwd_bwd": ([c_void_p, c_int64, c_void_p, c_int64, c_int, c_float, c_float, c_void_p, c_int64,
                                 c_void_p, c_void_p, c_int64, c_void_p], c_int),
+    "ps_sample_batch_workspace": ([c_int], c_int64),
+    "ps_sample_batch": ([c_void_p, c_int64, c_void_p, c_int64, c_int, c_uint64, c_uint64, c_void_p, c_void_p, c_int64,
+                         c_void_p, c_void_p], c_int),
     "ps_adam_step": ([c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_float, c_float, c_float, c_float, c_int64,
                       c_float, c_void_p], c_int),
 }
@@ -79,13 +83,12 @@ def lib():
 
 def _ensure_device():
     """The library links its own CUDA runtime; point it at torch's current device."""
-    global _device_set
     if not torch.cuda.is_available():
         raise NativeError("no CUDA device: the PinSage engine has no CPU fallback")
     dev = torch.cuda.current_device()
-    if _device_set != dev:
+    if getattr(_tls, "device", None) != dev:
         check(lib().ps_set_device(dev))
-        _device_set = dev
+        _tls.device = dev
     return dev
 
 
@@ -318,6 +321,22 @@ def margin_loss_fwd_bwd(emb, triples, margin, grad_scale, dup_counts, loss_out, 
                                        int(d), float(margin), float(grad_scale), _p(dup_counts, torch.int32), int(U),
                                        _p(loss_out, torch.float32), _p(demb, torch.float32),
                                        _ld(demb) if demb is not None else 0, _stream()))
+
+
+def sample_batch(positives, all_ids, n_items, B, seed, step, out=None):
+    """ps_sample_batch: int64 [B,3] (q, pos, neg) drawn on the device in one launch (no host sync)."""
+    _ensure_device()
+    if out is None:
+        out = torch.empty((B, 3), dtype=torch.int64, device="cuda")
+    ws = torch.empty(lib().ps_sample_batch_workspace(int(B)), dtype=torch.uint8, device="cuda")
+    check(lib().ps_sample_batch(_p(positives, torch.int64), int(positives.shape[0]), _p(all_ids, torch.int64), int(n_items), int(B),
+                                int(seed) & 0xFFFFFFFFFFFFFFFF, int(step) & 0xFFFFFFFFFFFFFFFF, _p(out, torch.int64),
+                                _p(ws), ws.numel(), None, _stream()))
+    return out
+
+
+def sample_batch_supported(P, n_items, B):
+    return 0 < B <= 2600 and 16 * B <= P < 0xFFFFFFFF and 16 * B <= n_items < (1 << 31)
 
 
 def adam_step(param, grad, exp_avg, exp_avg_sq, lr, beta1, beta2, eps, step, grad_scale=1.0):

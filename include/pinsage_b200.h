@@ -11,8 +11,9 @@
  *   - every function returns 0 on success or a negative PS_ERR_* code; the message is
  *     available from ps_last_error() (thread-local);
  *   - all pointers are DEVICE pointers owned by the caller unless stated otherwise; the
- *     library never allocates device memory behind the caller's back (ps_graph_t keeps
- *     the caller's CSR pointers, it does not copy them);
+ *     library never allocates device memory behind the caller's back, except inside the
+ *     opaque ps_graph_t: it keeps the caller's CSR pointers and owns a 4-byte copy of the
+ *     row offsets (when the graph has fewer than 2^32 entries) that halves the bytes per hop;
  *   - every launch is asynchronous on `stream` (a cudaStream_t passed as void*);
  *   - row-major matrices with an explicit leading dimension in ELEMENTS;
  *   - no global state; one host thread per device.
@@ -132,6 +133,19 @@ int ps_count_triples(const int32_t* triples, int64_t B, int64_t U, int32_t* dup_
 int ps_margin_loss_fwd_bwd(const float* emb, int64_t ld, const int32_t* triples, int64_t B, int d,
                            float margin, float grad_scale, const int32_t* dup_counts, int64_t U,
                            float* loss_out, float* demb, int64_t ldd, ps_stream_t stream);
+
+/* ---- K12: one training batch drawn on the device in one launch (pinsage_training.py:53-77,
+ *      easy negatives): out_batch int64 [B, 3] = (q, pos) of B distinct uniformly random rows of
+ *      positives [P, 2], and one negative per row: distinct uniformly random positions of all_ids
+ *      (NULL = identity) that are not a node of those pairs.  Same law as the reference's
+ *      randperm(P)[:B] / mask + randperm; draws are Philox4x32-10(counter = (candidate, phase,
+ *      step), key = seed), reproducible on the CPU (oracle.sample_batch_philox).
+ *      Limits: B <= 2600, 16*B <= P < 2^32-1, 16*B <= n_items < 2^31.  short_flag (may be NULL)
+ *      is set to 1 if the candidate stream ran out (not reachable within the limits). ---- */
+int64_t ps_sample_batch_workspace(int B); /* bytes of device scratch ps_sample_batch needs for batch size B */
+int ps_sample_batch(const int64_t* positives, int64_t P, const int64_t* all_ids, int64_t n_items, int B,
+                    uint64_t seed, uint64_t step, int64_t* out_batch, void* workspace, int64_t workspace_bytes,
+                    int* short_flag, ps_stream_t stream);
 
 /* ---- K13: Adam step on a flat fp32 parameter buffer (torch.optim.Adam defaults:
  *      betas, eps, no weight decay, no amsgrad; pinsage_training.py:147,191).

@@ -337,6 +337,36 @@ def check_batch_properties(batch, positives, n_items):
     assert not (set(neg.tolist()) & set(batch[:, :2].reshape(-1).tolist()))
 
 
+def sample_batch_philox(positives, n_items, B, seed, step):
+    """CPU restatement of ps_sample_batch (csrc/sampler.cu), which draws what the reference's
+    sample_positives_with_rep + sample_easy_negatives draw (pinsage_training.py:53-77): B distinct uniformly
+    random rows of `positives`, then B distinct uniformly random ids that are no node of those pairs.
+    Candidate c of phase ph = floor(r64 * range / 2^64), r64 = x0 << 32 | x1 of
+    Philox(counter=(c, ph, step_lo, step_hi), key=seed); first occurrences in stream order are kept."""
+    positives = np.asarray(positives, dtype=np.int64)
+    k0, k1 = np.uint32(seed & 0xFFFFFFFF), np.uint32((seed >> 32) & 0xFFFFFFFF)
+    s0, s1 = np.uint32(step & 0xFFFFFFFF), np.uint32((step >> 32) & 0xFFFFFFFF)
+
+    def stream(phase, rng, forbidden):
+        seen, out, c = set(forbidden), [], 0
+        while len(out) < B:
+            cs = np.arange(c, c + 4 * B + 64, dtype=np.uint32)
+            x0, x1, _, _ = philox4x32_10(cs, np.full_like(cs, phase), np.full_like(cs, s0), np.full_like(cs, s1), k0, k1)
+            for a, b in zip(x0.tolist(), x1.tolist()):
+                v = (((a << 32) | b) * rng) >> 64
+                if v not in seen:
+                    seen.add(v); out.append(v)
+                    if len(out) == B:
+                        break
+            c += 4 * B + 64
+        return np.array(out, dtype=np.int64)
+
+    rows = stream(0, positives.shape[0], ())
+    pairs = positives[rows]
+    neg = stream(1, n_items, set(pairs.reshape(-1).tolist()))
+    return np.concatenate([pairs, neg[:, None]], axis=1)
+
+
 def hit_rate(knn_mat, test_positives, K):
     """`hit_rate` (eval.py:227-238): fraction of test pairs (q, pos) with pos among the
     first K neighbours of q."""

@@ -254,3 +254,39 @@ def test_adam_matches_torch(nat):
         ref.grad = g.clone(); opt.step()
         nat.adam_step(p, g, m, v, 1e-3, 0.9, 0.999, 1e-8, step)
     assert torch.allclose(p, ref.data, rtol=1e-5, atol=1e-7)
+
+
+@pytest.mark.parametrize("B,P,n_items", [(128, 5000, 4324), (1024, 200_000, 50_000), (2600, 60_000, 41_600)])
+def test_sample_batch_bit_exact_vs_oracle(B, P, n_items):
+    """K12: the one-launch device batch sampler equals its CPU restatement bit for bit and has the properties the
+    reference's sample_batch guarantees (distinct positive rows, distinct negatives outside the pairs)."""
+    import ps_native as nat
+    from oracle import oracle
+    rng = np.random.RandomState(B)
+    positives = rng.randint(0, n_items, size=(P, 2)).astype(np.int64)
+    pos_d = torch.from_numpy(positives).cuda()
+    ids = torch.arange(n_items, device="cuda")
+    for step in (1, 2, 77):
+        got = nat.sample_batch(pos_d, ids, n_items, B, seed=0xABCDEF12345, step=step).cpu().numpy()
+        want = oracle.sample_batch_philox(positives, n_items, B, 0xABCDEF12345, step)
+        assert np.array_equal(got, want)
+        oracle.check_batch_properties(got, positives, n_items)
+    a = nat.sample_batch(pos_d, ids, n_items, B, seed=1, step=1).cpu().numpy()
+    b = nat.sample_batch(pos_d, None, n_items, B, seed=1, step=2).cpu().numpy()
+    assert not np.array_equal(a, b)
+
+
+def test_sample_batch_uniform():
+    """Negatives and positive rows are uniform: chi-square over 64 buckets on 200 batches."""
+    import ps_native as nat
+    n_items, P, B = 65_536, 131_072, 1024
+    positives = torch.stack([torch.arange(P) % n_items, (torch.arange(P) * 7 + 3) % n_items], 1).cuda()
+    ids = torch.arange(n_items, device="cuda")
+    neg = np.zeros(64); row = np.zeros(64)
+    for step in range(200):
+        b = nat.sample_batch(positives, ids, n_items, B, seed=5, step=step).cpu().numpy()
+        neg += np.bincount(b[:, 2] * 64 // n_items, minlength=64)
+        row += np.bincount((b[:, 0] % 64), minlength=64)  # q = row index mod n_items: buckets of the row index
+    for h in (neg, row):
+        exp = h.sum() / 64
+        assert ((h - exp) ** 2 / exp).sum() < 130  # chi2(63) 99.99th percentile ~ 115

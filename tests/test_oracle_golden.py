@@ -170,3 +170,16 @@ def test_metrics_and_knn(golden):
     w, nidx = oracle.knn_from_emb(g["knn_emb"], np.arange(300), 10)
     assert np.array_equal(nidx.numpy(), g["knn_n"])
     assert np.allclose(w.numpy(), g["knn_w"], rtol=1e-5, atol=1e-6)
+
+
+def test_sample_batch_philox_properties():
+    """The oracle's restatement of the device batch sampler has the reference's sample_batch guarantees
+    (pinsage_training.py:53-77) and is reproducible."""
+    rng = np.random.RandomState(0)
+    positives = rng.randint(0, 3000, size=(4000, 2)).astype(np.int64)
+    a = oracle.sample_batch_philox(positives, 3000, 128, seed=9, step=1)
+    b = oracle.sample_batch_philox(positives, 3000, 128, seed=9, step=1)
+    c = oracle.sample_batch_philox(positives, 3000, 128, seed=9, step=2)
+    assert np.array_equal(a, b) and not np.array_equal(a, c)
+    oracle.check_batch_properties(a, positives, 3000)
+    assert a.shape == (128, 3)
