@@ -92,15 +92,20 @@ aggregate_bwd_kernel(const float* __restrict__ dcat, int64_t ldcat, int col_off,
                      const int32_t* __restrict__ seg_off, const int32_t* __restrict__ chunk_off, int chunk_pairs,
                      const int32_t* __restrict__ pair_q, const float* __restrict__ nbw,
                      const float* __restrict__ inv_wsum, int T,
-                     float* __restrict__ z, int64_t ldz, int64_t n_zrows, float* __restrict__ partial) {
+                     float* __restrict__ z, int64_t ldz, int64_t n_zrows, float* __restrict__ partial,
+                     const int32_t* __restrict__ chunk_row) {
     const int lane = threadIdx.x & 31;
     const int64_t chunk = static_cast<int64_t>(blockIdx.x) * kWarps + (threadIdx.x >> 5);
     if (chunk >= __ldg(chunk_off + n_zrows)) return;
-    // row that owns this chunk: the last u with chunk_off[u] <= chunk
+    // row that owns this chunk: the last u with chunk_off[u] <= chunk (precomputed by the caller, else searched)
     int64_t lo = 0, hi = n_zrows;
-    while (hi - lo > 1) {
-        const int64_t mid = (lo + hi) >> 1;
-        if (__ldg(chunk_off + mid) <= chunk) lo = mid; else hi = mid;
+    if (chunk_row != nullptr) {
+        lo = __ldg(chunk_row + chunk);
+    } else {
+        while (hi - lo > 1) {
+            const int64_t mid = (lo + hi) >> 1;
+            if (__ldg(chunk_off + mid) <= chunk) lo = mid; else hi = mid;
+        }
     }
     const int64_t u = lo;
     const int first = __ldg(chunk_off + u), n_chunks = __ldg(chunk_off + u + 1) - first;
@@ -149,16 +154,18 @@ aggregate_bwd_kernel(const float* __restrict__ dcat, int64_t ldcat, int col_off,
             }
         }
     }
+    // z rows and partials stream through (read once / written once): evict-first keeps L2 for the dcat rows,
+    // which every z-row of a target's neighbourhood re-reads
     if (n_chunks == 1) {
         float* zr = z + u * ldz;
 #pragma unroll
         for (int c = 0; c < CH; ++c) {
             const int col = (c * 32 + lane) * 4;
             if (col < dh) {
-                const float4 y = *reinterpret_cast<const float4*>(zr + col);
-                *reinterpret_cast<float4*>(zr + col) =
-                    make_float4(acc[c].x * ps_leaky_grad_from_out(y.x), acc[c].y * ps_leaky_grad_from_out(y.y),
-                                acc[c].z * ps_leaky_grad_from_out(y.z), acc[c].w * ps_leaky_grad_from_out(y.w));
+                const float4 y = __ldcs(reinterpret_cast<const float4*>(zr + col));
+                __stcs(reinterpret_cast<float4*>(zr + col),
+                       make_float4(acc[c].x * ps_leaky_grad_from_out(y.x), acc[c].y * ps_leaky_grad_from_out(y.y),
+                                   acc[c].z * ps_leaky_grad_from_out(y.z), acc[c].w * ps_leaky_grad_from_out(y.w)));
             }
         }
     } else {
@@ -335,7 +342,8 @@ extern "C" int ps_aggregate_fwd(const float* hin, int64_t ld_hin, const int32_t*
 extern "C" int ps_aggregate_bwd(const float* dcat, int64_t ldcat, int col_off, int dh, const int32_t* seg_off,
                                 const int32_t* chunk_off, int chunk_pairs, int64_t max_chunks,
                                 const int32_t* pair_q, const float* nbw, const float* inv_wsum, int T,
-                                float* z, int64_t ldz, int64_t n_zrows, float* partial_ws, ps_stream_t stream_) {
+                                float* z, int64_t ldz, int64_t n_zrows, float* partial_ws, const int32_t* chunk_row,
+                                ps_stream_t stream_) {
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     PS_REQUIRE(dcat && seg_off && chunk_off && pair_q && nbw && inv_wsum && z && partial_ws, "null pointer");
     PS_REQUIRE(dh > 0 && dh % 4 == 0 && col_off % 4 == 0 && ldcat % 4 == 0 && ldz % 4 == 0 && T > 0, "bad shape");
@@ -346,7 +354,7 @@ extern "C" int ps_aggregate_bwd(const float* dcat, int64_t ldcat, int col_off, i
         const unsigned blocks = static_cast<unsigned>(ps_ceil_div(max_chunks, kWarps));
         PS_DISPATCH_CH(dh, (aggregate_bwd_kernel<CH><<<blocks, kWarps * 32, 0, stream>>>(
                                dcat, ldcat, col_off, dh, seg_off, chunk_off, chunk_pairs, pair_q, nbw, inv_wsum, T, z, ldz,
-                               n_zrows, partial_ws)));
+                               n_zrows, partial_ws, chunk_row)));
         PS_LAUNCH_CHECK();
     }
     const unsigned rblocks = static_cast<unsigned>(ps_ceil_div(n_zrows, kWarps));

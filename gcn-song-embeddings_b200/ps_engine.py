@@ -75,6 +75,7 @@ class LayerPlan:
     seg_off: Optional[torch.Tensor] = None  # int32 [nz+1]  (backward)
     pair_q: Optional[torch.Tensor] = None   # int32 [n*T]   (backward)
     chunk_off: Optional[torch.Tensor] = None  # int32 [nz+1] first work chunk of every z-row (backward)
+    chunk_row: Optional[torch.Tensor] = None  # int32 [max_chunks] z-row of every work chunk (backward)
 
 
 @dataclass
@@ -138,6 +139,7 @@ def build_plan(top: torch.Tensor, n_layers: int, T: int, table: NeighborTable, n
             # segment starts of the sorted keys (no bincount: it reads its maximum back to the host)
             lp.seg_off = torch.searchsorted(skeys, torch.arange(nz + 1, dtype=torch.int32, device=flat.device)).to(torch.int32)
             lp.chunk_off = nat.aggregate_bwd_chunks(lp.seg_off)
+            lp.chunk_row = nat.aggregate_bwd_chunk_rows(lp.chunk_off, flat.numel(), nz)
         plan.layers[l] = lp
         cur = nxt
     return plan
@@ -155,7 +157,7 @@ class Prepared:
     def tensors(self):
         out = [self.batch, self.triples, self.counts, self.plan.top]
         for lp in self.plan.layers:
-            out += [t for t in (lp.self_rows, lp.nbz, lp.w, lp.zrows, lp.seg_off, lp.pair_q, lp.chunk_off) if t is not None]
+            out += [t for t in (lp.self_rows, lp.nbz, lp.w, lp.zrows, lp.seg_off, lp.pair_q, lp.chunk_off, lp.chunk_row) if t is not None]
         return out
 
 
@@ -258,7 +260,7 @@ class Engine:
             nat.colsum(d_pre, grads[pre + "W.bias"])
             d_cat = torch.empty((lp.n, din + dh), dtype=torch.float32, device="cuda")
             nat.gemm(d_pre, conv.W.weight, d_cat, lp.n, din + dh, do, q_kmajor=False, tag=f"gemm_w_dgrad_l{l}")
-            nat.aggregate_bwd(d_cat, din, dh, lp.seg_off, lp.pair_q, lp.w, inv_wsum, lp.w.shape[1], z, chunk_off=lp.chunk_off, tag=f"aggregate_bwd_l{l}")  # z := dZ_pre
+            nat.aggregate_bwd(d_cat, din, dh, lp.seg_off, lp.pair_q, lp.w, inv_wsum, lp.w.shape[1], z, chunk_off=lp.chunk_off, chunk_row=lp.chunk_row, tag=f"aggregate_bwd_l{l}")  # z := dZ_pre
             nat.gemm(z, h_in, grads[pre + "Q.weight"], dh, din, lp.nz, p_kmajor=False, q_kmajor=False,
                      q_rows=lp.zrows, accumulate=True, splits=_splits_for(dh, din, lp.nz), tag=f"gemm_q_wgrad_l{l}")
             nat.colsum(z, grads[pre + "Q.bias"])

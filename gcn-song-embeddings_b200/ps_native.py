@@ -39,7 +39,7 @@ _SIGNATURES = {
     "ps_aggregate_fwd": ([c_void_p, c_int64, c_void_p, c_int, c_void_p, c_int64, c_void_p, c_void_p, c_int, c_int,
                           c_int64, c_void_p, c_int64, c_void_p, c_void_p], c_int),
     "ps_aggregate_bwd": ([c_void_p, c_int64, c_int, c_int, c_void_p, c_void_p, c_int, c_int64, c_void_p, c_void_p,
-                          c_void_p, c_int, c_void_p, c_int64, c_int64, c_void_p, c_void_p], c_int),
+                          c_void_p, c_int, c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_void_p], c_int),
     "ps_norm_leaky_bwd": ([c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_int64, c_int, c_void_p], c_int),
     "ps_l2norm_rows": ([c_void_p, c_int64, c_int64, c_int, c_void_p, c_void_p], c_int),
     "ps_leaky_bwd": ([c_void_p, c_void_p, c_int64, c_void_p], c_int),
@@ -270,8 +270,15 @@ def aggregate_bwd_chunks(seg_off, chunk_pairs=AGG_BWD_CHUNK):
     return chunk_off
 
 
+def aggregate_bwd_chunk_rows(chunk_off, pairs, nz, chunk_pairs=AGG_BWD_CHUNK):
+    """chunk_row int32 [max_chunks]: the z-row owning every chunk (device index arithmetic, no sync)."""
+    max_chunks = pairs // chunk_pairs + nz
+    q = torch.arange(max_chunks, dtype=torch.int32, device=chunk_off.device)
+    return (torch.searchsorted(chunk_off, q, right=True) - 1).to(torch.int32)
+
+
 def aggregate_bwd(dcat, col_off, dh, seg_off, pair_q, nbw, inv_wsum, T, z, chunk_off=None, chunk_pairs=AGG_BWD_CHUNK,
-                  tag="aggregate_bwd"):
+                  chunk_row=None, tag="aggregate_bwd"):
     pairs, nz = pair_q.numel(), z.shape[0]
     if chunk_off is None:
         chunk_off = aggregate_bwd_chunks(seg_off, chunk_pairs)
@@ -282,7 +289,8 @@ def aggregate_bwd(dcat, col_off, dh, seg_off, pair_q, nbw, inv_wsum, T, z, chunk
         check(lib().ps_aggregate_bwd(_p(dcat, torch.float32), _ld(dcat), int(col_off), int(dh),
                                      _p(seg_off, torch.int32), _p(chunk_off, torch.int32), int(chunk_pairs), int(max_chunks),
                                      _p(pair_q, torch.int32), _p(nbw, torch.float32), _p(inv_wsum, torch.float32), int(T),
-                                     _p(z, torch.float32), _ld(z), int(nz), _p(ws, torch.float32), _stream()))
+                                     _p(z, torch.float32), _ld(z), int(nz), _p(ws, torch.float32),
+                                     _p(chunk_row, torch.int32), _stream()))
 
 
 def norm_leaky_bwd(h, norm, dh, dpre):

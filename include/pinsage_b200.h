@@ -101,11 +101,14 @@ int ps_aggregate_fwd(const float* hin, int64_t ld_hin, const int32_t* self_rows,
  *      pairs gets zeros).  Segments are cut into chunks of at most chunk_pairs pairs, one
  *      warp each: chunk_off[u] = sum_{v<u} ceil(len(v) / chunk_pairs), int32 [n_zrows+1];
  *      max_chunks >= chunk_off[n_zrows] sizes the launch (no host sync needed) and
- *      partial_ws holds max_chunks * dh floats of scratch for rows that span several chunks. ---- */
+ *      partial_ws holds max_chunks * dh floats of scratch for rows that span several chunks.
+ *      chunk_row (optional, int32 [max_chunks]): the z-row that owns every chunk
+ *      (last u with chunk_off[u] <= chunk); NULL = searched per chunk. ---- */
 int ps_aggregate_bwd(const float* dcat, int64_t ldcat, int col_off, int dh,
                      const int32_t* seg_off, const int32_t* chunk_off, int chunk_pairs, int64_t max_chunks,
                      const int32_t* pair_q, const float* nbw, const float* inv_wsum, int T,
-                     float* z, int64_t ldz, int64_t n_zrows, float* partial_ws, ps_stream_t stream);
+                     float* z, int64_t ldz, int64_t n_zrows, float* partial_ws, const int32_t* chunk_row,
+                     ps_stream_t stream);
 /* backward of  h = y / ||y||,  y = leaky_relu(pre)  (pinsage_model.py:209-210):
  *   dpre = leaky'(h) * (dh - h * (h . dh)) / norm */
 int ps_norm_leaky_bwd(const float* h, int64_t ldh, const float* norm, const float* dh, int64_t lddh,

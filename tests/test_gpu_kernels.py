@@ -169,6 +169,12 @@ def test_aggregate_bwd_skewed_segments(nat):
     again = z.clone()
     nat.aggregate_bwd(dcat, din, dh, seg, order.to(torch.int32), w, inv, T, again, chunk_pairs=64)
     assert torch.equal(again, outs[0])  # deterministic (no atomics)
+    # precomputed chunk -> row map (what the engine passes) == the in-kernel search, bit for bit
+    mapped = z.clone()
+    coff = nat.aggregate_bwd_chunks(seg, 64)
+    crow = nat.aggregate_bwd_chunk_rows(coff, flat.numel(), nz, 64)
+    nat.aggregate_bwd(dcat, din, dh, seg, order.to(torch.int32), w, inv, T, mapped, chunk_off=coff, chunk_pairs=64, chunk_row=crow)
+    assert torch.equal(mapped, outs[0])
 
 
 def test_rowwise_kernels(nat):
