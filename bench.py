@@ -222,6 +222,8 @@ def run_ours(args, wl):
         raise SystemExit("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm")
     dev = torch.device("cuda", local)
     peaks = load_peaks()
+    if args.tc_waves:
+        ps_native.lib().ps_gemm_tc_waves(args.tc_waves)
     torch.manual_seed(1000 + rank)
     N, C, din, T, B, L = wl["n_tracks"], wl["n_cols"], wl["din"], wl["T"], wl["batch"], wl["n_layers"]
 
@@ -376,6 +378,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cfg3", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--tc-waves", type=int, default=0, help="override ps_gemm_tc_waves (development)")
     ap.add_argument("--torch-profile", default=None, help="write a torch.profiler kernel table of 3 extra steps here")
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]

@@ -31,6 +31,7 @@ constexpr int BK = 32;                  // floats per k-block = one 128-byte swi
 constexpr int kProducerThreads = 256;
 constexpr int kThreads = 640;
 constexpr uint32_t kHiMask = 0xFFFFE000u;  // keep sign, exponent and the 10 tf32 mantissa bits
+constexpr int kEpiStride = 20;             // floats per staged row: 16 columns + 4 pad (conflict-free STS.128)
 
 struct TcArgs {
     const float* P; int64_t ldp; const int32_t* p_rows;
@@ -41,6 +42,7 @@ struct TcArgs {
     int act, l2norm, accumulate;
     int kb_per_split;   // k-blocks (of BK) per split
     int64_t mt, nt, zs;  // work grid: M tiles x N tiles x K splits
+    const uint8_t* bpack;  // BPACK kernels: hi/lo images of the Q operand, one [2][BN x 128 B] block per (n-tile, k-block)
 };
 
 // ---------------------------------------------------------------- PTX wrappers
@@ -65,6 +67,14 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     while (!mbar_try_wait(bar, parity)) {
         if (clock64() - t0 > 2000000000ll) __trap();
     }
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+// 1-D bulk copy global -> shared (TMA engine, no tensor map): completes `bytes` on the mbarrier
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
 }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
@@ -257,8 +267,12 @@ __device__ __forceinline__ Work decode_work(const TcArgs& a, int64_t w, int bn) 
 // registers away: setmaxnreg works on whole warpgroups).  Persistent: every role walks the same list of work
 // items (blockIdx.x, + gridDim.x, ...), so the producers and the MMA warp run ahead into the next tile while
 // the accumulate warps are still storing the previous one.
-template <bool PK, bool QK, int BN>
+// BPACK: the Q operand (a weight matrix) was split into hi/lo and laid out as K-major SWIZZLE_128B tile images by
+// pack_b_kernel; one thread streams the image of every k-block into the stage with ONE bulk copy, and the eight
+// producer warps only move the activation operand, double-buffered in registers across k-blocks and tiles.
+template <bool PK, bool QK, int BN, bool BPACK>
 __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(TcArgs a) {
+    static_assert(!BPACK || (PK && QK), "packed-B kernels take a K-major P and lay Q out K-major");
     constexpr int STAGES = BN == 256 ? 2 : 3;
     constexpr int HALF = BN / 2;            // columns owned by one epilogue thread
     constexpr int CHUNK_KB = 2;             // k-blocks accumulated in TMEM before the fp32 register drain
@@ -270,6 +284,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(TcArgs a) {
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
     float* ss_buf = reinterpret_cast<float*>(tmem_slot + 4);  // [2 parities][2 halves][128] partial sums of squares (l2norm)
     float* bias_s = ss_buf + 2 * 2 * 128;                     // [2 parities][BN] bias of the current tile
+    float* epi_buf = bias_s + 2 * BN;                         // [8 warps][32 rows][kEpiStride] output staging (coalesced stores)
     const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + STAGES);
     const uint32_t tfull0 = smem_u32(bars + 2 * STAGES), tempty0 = smem_u32(bars + 2 * STAGES + 2);
 
@@ -277,7 +292,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(TcArgs a) {
     const int64_t total_work = a.mt * a.nt * a.zs;
 
     if (tid == 0) {
-        for (int s = 0; s < STAGES; ++s) { mbar_init(full0 + 8 * s, kProducerThreads); mbar_init(empty0 + 8 * s, 1); }
+        for (int s = 0; s < STAGES; ++s) { mbar_init(full0 + 8 * s, kProducerThreads + (BPACK ? 1 : 0)); mbar_init(empty0 + 8 * s, 1); }
         for (int b = 0; b < 2; ++b) { mbar_init(tfull0 + 8 * b, 1); mbar_init(tempty0 + 8 * b, 8); }
         fence_barrier_init();
     }
@@ -325,6 +340,60 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(TcArgs a) {
                     umma_commit(tfull0 + 8 * buf);  // publishes the chunk to the accumulate warps
                     ++gc;
                 }
+            }
+        }
+        // ------------------------------------------------ packed-B stream (one lane of warp 17)
+        if (BPACK && warp == 17 && lane == 0) {
+            const int64_t nkb = (a.K + BK - 1) / BK;
+            int stage = 0; uint32_t phase = 0;
+            for (int64_t w = blockIdx.x; w < total_work; w += gridDim.x) {
+                const Work wk = decode_work(a, w, BN);
+                const uint8_t* src = a.bpack + ((wk.n0 / BN) * nkb + wk.kb_begin) * static_cast<int64_t>(2 * B_BYTES);
+                for (int kb = 0; kb < wk.num_kb; ++kb, src += 2 * B_BYTES) {
+                    mbar_wait(empty0 + 8 * stage, phase ^ 1);
+                    mbar_arrive_expect_tx(full0 + 8 * stage, 2 * B_BYTES);
+                    bulk_g2s(smem_u32(smem + stage * STAGE_BYTES + 2 * A_BYTES), src, 2 * B_BYTES, full0 + 8 * stage);
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp >= 8 && BPACK) {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+        // ------------------------------------------------ producers, activation operand only (8 warps)
+        const int t = tid - 8 * 32;
+        using OpA = Operand<true, BM, true>;
+        constexpr int NJ = OpA::NJ;
+        OpA op;                       // the LOAD cursor: one k-block ahead of the stores, across tile boundaries
+        int64_t lw = blockIdx.x;
+        int lkb = 0;
+        Work lwk = decode_work(a, lw < total_work ? lw : 0, BN);
+        float4 cur[NJ], nxt[NJ];
+        if (lw < total_work) {
+            op.init(a.P, a.ldp, a.p_rows, lwk.m0, a.M, t);
+            op.template load<0, NJ>(cur, static_cast<int64_t>(lwk.kb_begin) * BK, a.K);
+        }
+        const uint32_t off0 = op.off0;  // shared-memory offsets depend on the thread only, not on the tile
+        int stage = 0; uint32_t phase = 0;
+        for (int64_t w = blockIdx.x; w < total_work; w += gridDim.x) {
+            const Work wk = decode_work(a, w, BN);
+            for (int kb = 0; kb < wk.num_kb; ++kb) {
+                // advance the load cursor and issue the next k-block's loads before waiting for the stage
+                bool have_next = true;
+                if (++lkb == lwk.num_kb) {
+                    lw += gridDim.x; lkb = 0;
+                    have_next = lw < total_work;
+                    if (have_next) { lwk = decode_work(a, lw, BN); op.init(a.P, a.ldp, a.p_rows, lwk.m0, a.M, t); }
+                }
+                if (have_next) op.template load<0, NJ>(nxt, static_cast<int64_t>(lwk.kb_begin + lkb) * BK, a.K);
+                mbar_wait(empty0 + 8 * stage, phase ^ 1);
+                uint8_t* st = smem + stage * STAGE_BYTES;
+#pragma unroll
+                for (int j = 0; j < NJ; ++j) split_store(st, st + A_BYTES, off0 + j * OpA::kStep, cur[j]);
+                fence_proxy_async();
+                mbar_arrive(full0 + 8 * stage);
+                if (++stage == STAGES) { stage = 0; phase ^= 1; }
+#pragma unroll
+                for (int j = 0; j < NJ; ++j) cur[j] = nxt[j];
             }
         }
     } else if (warp >= 8) {
@@ -413,19 +482,37 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(TcArgs a) {
                 inv_norm = 1.f / nrm;
                 if (half == 0 && row_ok && a.norm_out) a.norm_out[row] = nrm;
             }
-            if (row_ok) {
-                float* dst = a.C + row * a.ldc + col0;
+            // Stores go through a per-warp shared-memory transpose, 16 columns at a time: a thread owns one output
+            // row, and writing it directly would touch 32 rows x 16 B per instruction (half sectors, 32 LSU
+            // wavefronts).  Staged, an instruction writes 8 rows x 64 contiguous bytes (full sectors).
+            {
+                float* wb = epi_buf + warp * (32 * kEpiStride);
+                const int rr = lane >> 2, cc = (lane & 3) * 4;
+                const int64_t row_base = wk.m0 + quarter * 32;
 #pragma unroll
-                for (int j = 0; j < HALF; j += 4) {
-                    if (col0 + j < a.N) {  // N % 4 == 0: a float4 is all-or-nothing
-                        if (a.accumulate) {
-                            atomicAdd(dst + j + 0, acc[j + 0]); atomicAdd(dst + j + 1, acc[j + 1]);
-                            atomicAdd(dst + j + 2, acc[j + 2]); atomicAdd(dst + j + 3, acc[j + 3]);
-                        } else {
-                            *reinterpret_cast<float4*>(dst + j) = make_float4(acc[j] * inv_norm, acc[j + 1] * inv_norm,
-                                                                              acc[j + 2] * inv_norm, acc[j + 3] * inv_norm);
+                for (int blk = 0; blk < HALF / 16; ++blk) {
+#pragma unroll
+                    for (int q = 0; q < 4; ++q)
+                        *reinterpret_cast<float4*>(wb + lane * kEpiStride + 4 * q) =
+                            make_float4(acc[16 * blk + 4 * q] * inv_norm, acc[16 * blk + 4 * q + 1] * inv_norm,
+                                        acc[16 * blk + 4 * q + 2] * inv_norm, acc[16 * blk + 4 * q + 3] * inv_norm);
+                    __syncwarp();
+                    const int64_t gcol = col0 + 16 * blk + cc;
+#pragma unroll
+                    for (int p8 = 0; p8 < 4; ++p8) {
+                        const int r = 8 * p8 + rr;
+                        const float4 v = *reinterpret_cast<const float4*>(wb + r * kEpiStride + cc);
+                        const int64_t grow = row_base + r;
+                        if (grow < a.M && gcol < a.N) {  // N % 4 == 0: a float4 is all-or-nothing
+                            float* dst = a.C + grow * a.ldc + gcol;
+                            if (a.accumulate) {
+                                atomicAdd(dst + 0, v.x); atomicAdd(dst + 1, v.y); atomicAdd(dst + 2, v.z); atomicAdd(dst + 3, v.w);
+                            } else {
+                                *reinterpret_cast<float4*>(dst) = v;
+                            }
                         }
                     }
+                    __syncwarp();
                 }
             }
         }
@@ -435,11 +522,68 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(TcArgs a) {
     if (warp == 16) { tc_fence_after(); tmem_dealloc<2 * BN>(tmem_base); }
 }
 
-template <bool PK, bool QK, int BN>
-int launch_tc(const TcArgs& a, cudaStream_t stream) {
+// Split a weight operand into hi/lo and write the K-major SWIZZLE_128B tile images the BPACK kernels stream:
+// block (n-tile, k-block) -> [hi: BN rows x 128 B][lo: BN rows x 128 B]; row j = output column n0 + j, 16-byte
+// chunk c (k0 + 4c .. +3) stored at c ^ (j % 8), 8-row groups 1024 B apart.  Works from either source layout.
+template <int BN>
+__global__ void __launch_bounds__(256) pack_b_kernel(const float* __restrict__ Q, int64_t ldq, int q_kmajor, int64_t N, int64_t K,
+                                                     int64_t nkb, uint8_t* __restrict__ out) {
+    const int64_t tile = blockIdx.x;
+    const int64_t n0 = (tile / nkb) * BN, k0 = (tile % nkb) * BK;
+    uint8_t* hi = out + tile * (2 * BN * 128);
+    uint8_t* lo = hi + BN * 128;
+    for (int g = threadIdx.x; g < BN * 8; g += 256) {
+        const int j = q_kmajor ? g >> 3 : g % BN;
+        const int c = q_kmajor ? g & 7 : g / BN;
+        float v[4] = {0.f, 0.f, 0.f, 0.f};
+        const int64_t n = n0 + j;
+        if (n < N) {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const int64_t k = k0 + 4 * c + e;
+                if (k < K) v[e] = __ldg(q_kmajor ? Q + n * ldq + k : Q + k * ldq + n);
+            }
+        }
+        const uint32_t off = (j >> 3) * 1024 + (j & 7) * 128 + ((c ^ (j & 7)) << 4);
+        split_store(hi, lo, off, make_float4(v[0], v[1], v[2], v[3]));
+    }
+}
+
+// Scratch for the packed weight images: one buffer per (device, stream), grown on demand and reused by every later
+// call on that stream (stream order makes the reuse safe; cudaFree of an outgrown buffer waits for its readers).
+// cudaMallocAsync per call was measured to stall the host inside the training step.
+static int g_tc_waves = 1;
+
+struct PackSlot { int dev; cudaStream_t stream; void* ptr; size_t bytes; };
+static PackSlot g_pack_slots[16] = {};
+
+static int pack_scratch(cudaStream_t stream, size_t bytes, void** out) {
+    int dev = 0;
+    PS_CUDA_CHECK(cudaGetDevice(&dev));
+    PackSlot* slot = nullptr;
+    for (auto& s : g_pack_slots)
+        if (s.ptr != nullptr && s.dev == dev && s.stream == stream) { slot = &s; break; }
+    if (slot == nullptr)
+        for (auto& s : g_pack_slots)
+            if (s.ptr == nullptr) { slot = &s; break; }
+    if (slot == nullptr) slot = &g_pack_slots[0];  // more than 16 (device, stream) pairs: recycle
+    if (slot->ptr == nullptr || slot->dev != dev || slot->stream != stream || slot->bytes < bytes) {
+        if (slot->ptr != nullptr) PS_CUDA_CHECK(cudaFree(slot->ptr));
+        slot->ptr = nullptr;
+        const size_t want = bytes < (4u << 20) ? (4u << 20) : bytes;
+        PS_CUDA_CHECK(cudaMalloc(&slot->ptr, want));
+        slot->dev = dev; slot->stream = stream; slot->bytes = want;
+    }
+    *out = slot->ptr;
+    return PS_OK;
+}
+
+template <bool PK, bool QK, int BN, bool BPACK>
+int launch_tc(TcArgs a, int q_kmajor, cudaStream_t stream) {
     constexpr int STAGES = BN == 256 ? 2 : 3;
-    constexpr size_t smem = STAGES * (2 * BM * 128 + 2 * BN * 128) + (2 * STAGES + 4) * 8 + 16 + (2 * 2 * 128 + 2 * BN) * 4 + 1024;
-    auto kern = gemm_tc_kernel<PK, QK, BN>;
+    constexpr size_t smem = STAGES * (2 * BM * 128 + 2 * BN * 128) + (2 * STAGES + 4) * 8 + 16 + (2 * 2 * 128 + 2 * BN + 8 * 32 * kEpiStride) * 4 + 1024;
+    static_assert(smem <= 232448, "shared memory budget");
+    auto kern = gemm_tc_kernel<PK, QK, BN, BPACK>;
     static bool configured = false;
     static int sms = 148;
     if (!configured) {
@@ -449,14 +593,33 @@ int launch_tc(const TcArgs& a, cudaStream_t stream) {
         PS_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
         configured = true;
     }
+    void* pack = nullptr;
+    if (BPACK) {
+        const int64_t nkb = ps_ceil_div(a.K, BK);
+        const size_t bytes = static_cast<size_t>(a.nt * nkb) * 2 * BN * 128;
+        const int rc = pack_scratch(stream, bytes, &pack);
+        if (rc != PS_OK) return rc;
+        pack_b_kernel<BN><<<static_cast<unsigned>(a.nt * nkb), 256, 0, stream>>>(a.Q, a.ldq, q_kmajor, a.N, a.K, nkb, static_cast<uint8_t*>(pack));
+        PS_LAUNCH_CHECK();
+        a.bpack = static_cast<const uint8_t*>(pack);
+    }
+    // Persistent CTAs, but bounded: with >= 8 work items per SM the grid is g_tc_waves x SMs, so every CTA retires
+    // after 1/g_tc_waves of its SM's share and a pending higher-priority CTA (the side-stream batch preparation of the
+    // next training step) gets the SM within a fraction of the GEMM instead of after all of it.
     const int64_t total = a.mt * a.nt * a.zs;
-    const unsigned grid = static_cast<unsigned>(total < sms ? total : sms);  // persistent: one CTA per SM
+    int64_t grid64 = total < sms ? total : sms;
+    if (g_tc_waves > 1 && total >= static_cast<int64_t>(sms) * 8 * g_tc_waves) grid64 = static_cast<int64_t>(sms) * g_tc_waves;
+    const unsigned grid = static_cast<unsigned>(grid64);
     kern<<<grid, kThreads, smem, stream>>>(a);
     PS_LAUNCH_CHECK();
     return PS_OK;
 }
 
 }  // namespace
+
+extern "C" int ps_gemm_tc_waves(int waves) { const int old = g_tc_waves; if (waves >= 1 && waves <= 64) g_tc_waves = waves; return old; }
+static bool g_tc_pack = true;
+extern "C" int ps_gemm_tc_pack(int on) { const int old = g_tc_pack; if (on == 0 || on == 1) g_tc_pack = on != 0; return old; }
 
 // Returns PS_ERR_UNSUPPORTED (without setting an error) when the shape is outside what this
 // path covers; the dispatcher then uses the CUDA-core kernel.
@@ -482,16 +645,19 @@ int ps_gemm_tc_launch(const float* P, int64_t ldp, int p_kmajor, const int32_t* 
     if (!accumulate && K > 4 * kMaxChainK) return PS_ERR_UNSUPPORTED;
     if (accumulate && ps_ceil_div(K, splits < 1 ? 1 : splits) > kMaxChainK) splits = static_cast<int>(ps_ceil_div(K, kMaxChainK));
     const int BN = (N > 128) ? 256 : 128;
-    TcArgs a{P, ldp, p_rows, Q, ldq, q_rows, C, ldc, M, N, K, bias, norm_out, act, l2norm, accumulate, 0, 0, 0, 0};
+    TcArgs a{P, ldp, p_rows, Q, ldq, q_rows, C, ldc, M, N, K, bias, norm_out, act, l2norm, accumulate, 0, 0, 0, 0, nullptr};
     const int64_t num_kb = ps_ceil_div(K, BK);
     if (splits < 1) splits = 1;
     a.kb_per_split = static_cast<int>(ps_ceil_div(num_kb, splits));
     a.zs = ps_ceil_div(num_kb, a.kb_per_split);
     a.mt = ps_ceil_div(M, BM);
     a.nt = ps_ceil_div(N, BN);
+    // weight operand (no gather, no split-K) against a tall K-major activation: pre-packed hi/lo images + bulk copies
+    if (g_tc_pack && p_kmajor && q_rows == nullptr && !accumulate && a.zs == 1 && M >= 1024)
+        return BN == 256 ? launch_tc<true, true, 256, true>(a, q_kmajor, stream) : launch_tc<true, true, 128, true>(a, q_kmajor, stream);
 #define PS_TC_CASE(pk, qk)                                                         \
     if (static_cast<bool>(p_kmajor) == pk && static_cast<bool>(q_kmajor) == qk)     \
-        return BN == 256 ? launch_tc<pk, qk, 256>(a, stream) : launch_tc<pk, qk, 128>(a, stream);
+        return BN == 256 ? launch_tc<pk, qk, 256, false>(a, q_kmajor, stream) : launch_tc<pk, qk, 128, false>(a, q_kmajor, stream);
     PS_TC_CASE(true, true)
     PS_TC_CASE(true, false)
     PS_TC_CASE(false, true)

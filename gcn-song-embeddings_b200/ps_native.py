@@ -29,6 +29,8 @@ _SIGNATURES = {
     "ps_last_error": ([], c_char_p),
     "ps_set_device": ([c_int], c_int),
     "ps_gemm_backend": ([c_int], c_int),
+    "ps_gemm_tc_pack": ([c_int], c_int),
+    "ps_gemm_tc_waves": ([c_int], c_int),
     "ps_graph_create": ([c_void_p, c_void_p, c_int64, c_int64, c_int64, ctypes.POINTER(c_void_p), c_void_p], c_int),
     "ps_graph_destroy": ([c_void_p], c_int),
     "ps_walk_topt": ([c_void_p, c_void_p, c_int64, c_int, c_double, c_int, c_int, c_uint64,
@@ -243,6 +245,11 @@ def _gemm(P, Q, C, M, N, K, p_kmajor, q_kmajor, p_rows, q_rows, bias, act, l2nor
 def gemm_backend(mode: int) -> int:
     """0 = tcgen05 3xTF32 (default), 1 = CUDA-core fp32; returns the previous mode."""
     return lib().ps_gemm_backend(int(mode))
+
+
+def gemm_tc_pack(on: int) -> int:
+    """1 = pre-packed weight operands + bulk copies on the tensor-core path (default), 0 = off; returns the previous setting."""
+    return lib().ps_gemm_tc_pack(int(on))
 
 
 def aggregate_fwd(hin, self_rows, din, z, nbz, nbw, dh, cat, inv_wsum, tag="aggregate_fwd"):

@@ -14,6 +14,7 @@
  *     library never allocates device memory behind the caller's back, except inside the
  *     opaque ps_graph_t: it keeps the caller's CSR pointers and owns a 4-byte copy of the
  *     row offsets (when the graph has fewer than 2^32 entries) that halves the bytes per hop;
+ *     ps_gemm keeps one small scratch buffer per (device, stream) for packed weight images;
  *   - every launch is asynchronous on `stream` (a cudaStream_t passed as void*);
  *   - row-major matrices with an explicit leading dimension in ELEMENTS;
  *   - no global state; one host thread per device.
@@ -84,6 +85,13 @@ int ps_gemm(const float* P, int64_t ldp, int p_kmajor, const int32_t* p_rows,
  * error-compensated split wherever the shape allows (CUDA cores otherwise), 1 = CUDA-core
  * fp32 only.  Returns the previous mode (any other argument just queries). */
 int ps_gemm_backend(int mode);
+/* Tuning knob of the tensor-core path: 1 (default) = weight operands (no gather, no split-K, M >= 1024) are
+ * pre-split into hi/lo tile images once per call and streamed with bulk copies; 0 = every operand goes through
+ * the producer warps.  Results are identical either way.  Returns the previous setting. */
+int ps_gemm_tc_pack(int on);
+/* Tuning knob: large tensor-core GEMMs launch waves x SMs persistent CTAs (default 1 = one CTA per SM; measured best on cfg3), so an SM is handed to a
+ * pending higher-priority stream after 1/waves of the GEMM.  1 = one CTA per SM.  Returns the previous value. */
+int ps_gemm_tc_waves(int waves);
 
 /* ---- K4+K6: neighbour gather + importance-weighted mean fused with the concat
  *      (pinsage_model.py:195-197,202,208):

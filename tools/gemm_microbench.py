@@ -7,9 +7,9 @@ import torch
 import ps_native as nat
 
 ap = argparse.ArgumentParser(); ap.add_argument("--backend", type=int, default=0); ap.add_argument("--iters", type=int, default=5)
-ap.add_argument("--only", default="")
+ap.add_argument("--only", default=""); ap.add_argument("--pack", type=int, default=1)
 args = ap.parse_args()
-nat._ensure_device(); nat.gemm_backend(args.backend)
+nat._ensure_device(); nat.gemm_backend(args.backend); nat.gemm_tc_pack(args.pack)
 torch.manual_seed(0)
 N_TAB = 1_000_000
 feat = torch.randn(N_TAB, 256, device="cuda")
@@ -43,4 +43,4 @@ for name, (M, N, K, pk, qk, gather, acc) in shapes.items():
         run()
     e1.record(); torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / args.iters
-    print(f"backend {args.backend}  {name:42s} {ms:8.3f} ms  {2.0 * M * N * K / ms / 1e9:8.1f} TFLOP/s", flush=True)
+    print(f"backend {args.backend} pack {args.pack}  {name:42s} {ms:8.3f} ms  {2.0 * M * N * K / ms / 1e9:8.1f} TFLOP/s", flush=True)
