@@ -45,6 +45,10 @@ WORKLOADS = {
     # BASELINE.json configs[2]
     "cfg3": dict(n_tracks=1_000_000, n_cols=200_000, n_edges=40_000_000, din=256, n_layers=2, T=50, batch=1024,
                  n_pos=10_000_000, ref_batch=8),
+    # BASELINE.json configs[3]: full-graph embedding inference sharded by node range (run with --mode infer)
+    "cfg4": dict(n_tracks=20_000_000, n_cols=4_000_000, n_edges=1_000_000_000, din=512, n_layers=3, T=50, batch=0, n_pos=0, ref_batch=0),
+    # the same inference path at 1/4 of the size (development)
+    "cfg4q": dict(n_tracks=5_000_000, n_cols=1_000_000, n_edges=250_000_000, din=512, n_layers=3, T=50, batch=0, n_pos=0, ref_batch=0),
     # small stand-in for quick checks (not a bench line)
     "micro": dict(n_tracks=20_000, n_cols=4_000, n_edges=400_000, din=256, n_layers=2, T=50, batch=256,
                   n_pos=200_000, ref_batch=8),
@@ -370,6 +374,63 @@ def run_ours(args, wl):
     return 0
 
 
+def run_inference(args, wl):
+    """--mode infer: full-graph embedding inference sharded by node range (BASELINE.json configs[3]); every rank
+    embeds its rows [lo, hi) with no communication (ps_dist.embed_shard).  nodes/s = N / max-over-ranks time of one
+    pass; the one-time neighbourhood precompute (walker over all N) is timed separately.  Not the headline bench line."""
+    import ps_dist
+    import ps_native
+    import ps_synth
+    import pinsage_model as psm
+    from oracle import oracle
+    rank, world, local = ps_dist.init_from_env()
+    N, C, din, T, L = wl["n_tracks"], wl["n_cols"], wl["din"], wl["T"], wl["n_layers"]
+    t0 = time.perf_counter()
+    g = ps_synth.make_graph(N, C, wl["n_edges"], seed=1234, device="cuda")
+    gh = g.device()
+    feats = ps_synth.features(N, din, seed=1, device="cuda")
+    torch.cuda.synchronize()
+    setup_s = time.perf_counter() - t0
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    out = ps_native.walk_topt(gh, torch.arange(N, device="cuda"), 500, 0.85, T, seed=7, want_i64=False, want_i32=True)
+    e1.record(); torch.cuda.synchronize()
+    walk_ms = e0.elapsed_time(e1)
+    from ps_engine import NeighborTable
+    table = NeighborTable.__new__(NeighborTable)
+    table.nodes, table.w, table.n, table.Tp, table.scratch = out["nodes_i32"], out["weights_f32"], N, T, {}
+    dims = (din, 512, 128)
+    model = psm.PinSageModel(g, N, L, dims, 500, 0.85, T, table)
+    model.load_state_dict(oracle.make_params(L, dims, np.random.RandomState(0)))  # seeded xavier weights, bias 0.3
+
+    class _T:  # the two attributes embed_shard reads
+        pass
+    tr = _T(); tr.rank, tr.world_size, tr.n, tr.model = rank, world, N, model
+    tr._feats = lambda: feats
+    times, stats = [], {}
+    for it in range(args.warmup + args.steps):
+        torch.cuda.synchronize(); ps_dist.barrier()
+        e0.record()
+        lo, hi, emb = ps_dist.embed_shard(tr, chunk=1 << 18, stats=stats)
+        e1.record(); torch.cuda.synchronize()
+        if it >= args.warmup:
+            times.append(e0.elapsed_time(e1))
+        checksum = float(emb.double().sum())
+        del emb
+    ms = ps_dist.max_over_ranks(sum(times) / len(times))
+    if rank == 0:
+        print(json.dumps({"metric": "pinsage_embed_nodes_per_sec", "value": round(N / (ms * 1e-3), 1), "unit": "nodes/s", "n_gpus": world,
+                          "steps": args.steps, "warmup": args.warmup, "ms_per_pass": round(ms, 2), "higher_is_better": True, "scaling": "strong",
+                          "dtype": "f32", "data": "synthetic",
+                          "config": {"workload": f"{args.workload}: {N} tracks / {C} playlists / {wl['n_edges']} edges, {din}-d features, {L} layers, T={T}, "
+                                                 f"node-range shards over {world} GPU(s), no communication", "rank0_rows": hi - lo, "rank0_closure": stats},
+                          "walk": {"steps_per_s": round(N * 500 / (walk_ms * 1e-3), 1), "ms": round(walk_ms, 2), "sources": N, "n_hops": 500, "T": T},
+                          "setup_s": round(setup_s, 1), "hbm_gb_allocated": round(torch.cuda.max_memory_allocated() / 1e9, 1),
+                          "checksum_rank0": checksum}), flush=True)
+    ps_dist.barrier()
+    return 0
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -377,11 +438,14 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cfg3", choices=sorted(WORKLOADS))
+    ap.add_argument("--mode", default="train", choices=["train", "infer"], help="infer = node-range sharded full-graph embedding (cfg4 / cfg4q)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--tc-waves", type=int, default=0, help="override ps_gemm_tc_waves (development)")
     ap.add_argument("--torch-profile", default=None, help="write a torch.profiler kernel table of 3 extra steps here")
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]
+    if args.mode == "infer":
+        return run_inference(args, wl)
     if args.impl == "reference":
         return run_reference(args, wl)
     if args.warmup < 3:

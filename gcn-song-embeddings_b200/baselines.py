@@ -1,7 +1,8 @@
 """PinSage-side slice of the reference's `baselines` module (reference:
 /root/reference/baselines.py:33-103, 281-377): the recommender ABCs, cosine kNN from
-embeddings (on the device, ps_knn), the per-track embedding loader and the PinSage wrapper.
-The competing recommenders (PPR / Jaccard / node2vec / implicit CF / GraphSAGE) are out of
+embeddings (on the device, ps_knn), the per-track embedding loader, the PinSage wrapper and the
+personalised-PageRank baseline (it is the same walker).
+The other competing recommenders (Jaccard / node2vec / implicit CF / GraphSAGE) are out of
 scope."""
 from __future__ import annotations
 
@@ -12,6 +13,7 @@ from abc import ABC, abstractmethod
 import torch
 from tqdm import tqdm
 
+import pinsage_model as psm
 from pinsage_training import PinSage
 from ps_knn import cosine_sim_ab, knn_from_emb  # noqa: F401  (re-exported reference names)
 
@@ -38,6 +40,33 @@ class EmbeddingModel(PredictionModel):
     @abstractmethod
     def embed(self, nodeset):
         pass
+
+
+class PersPageRank(PredictionModel):
+    """Nearest graph neighbours by personalised PageRank, i.e. random walks with restarts
+    (baselines.py:107-151).  The reference runs a copy of the PinSage walker in Python (n_hops 1000, alpha 0.85)
+    and takes topk of the dense visit-probability row; here knn() is one ps_walk_topt launch (walk + visit counts +
+    top-k fused on the device).  Order inside equal counts is (node id ascending); slots beyond the number of
+    visited nodes carry weight 0."""
+
+    def __init__(self):
+        self.n_hops = 1000
+        self.alpha = 0.85
+
+    def visit_prob(self, g, nodeset, n_hops, alpha):
+        """Dense float64 [len(nodeset), number_of_nodes] visit probabilities, self entry zeroed (baselines.py:114-143)."""
+        return psm.sample_neighborhood(g, _n_items(g), nodeset, n_hops, alpha)
+
+    def train(self, g, ids, train_set, test_set, features):
+        self.g = g
+        self.n_items = len(ids)
+
+    def knn(self, nodeset, k):
+        return psm.sample_neighborhood_topt(self.g, self.n_items, nodeset, self.n_hops, self.alpha, k)
+
+
+def _n_items(g):
+    return g.n_tracks if hasattr(g, "n_tracks") else g.number_of_nodes()
 
 
 def _load_embeddings(ids, load_dir):

@@ -116,13 +116,13 @@ def precompute_neighborhoods_topt(g, n_items, n_hops, alpha, T, path, seed=None)
     out = ps_native.walk_topt(pg.device(), torch.arange(n_items, device="cuda"), n_hops, alpha, T,
                               _next_seed() if seed is None else seed, want_i32=True)
     weights, nodes = out["weights"].cpu(), out["nodes"].cpu()
+    print(f"{n_items}/{n_items} done.\n{time.time() - t0}s elapsed.")
+    if path is not None:
+        torch.save((weights, nodes), path)  # plain tensors, the reference's file format (before anything is attached)
     # keep the engine-native device copy (int32 / float32) attached, so the trainer does not upload it again
     table = NeighborTable.__new__(NeighborTable)
     table.nodes, table.w, table.n, table.Tp, table.scratch = out["nodes_i32"], out["weights_f32"], n_items, T, {}
     weights._ps_table = table
-    print(f"{n_items}/{n_items} done.\n{time.time() - t0}s elapsed.")
-    if path is not None:
-        torch.save((weights, nodes), path)
     return (weights, nodes)
 
 

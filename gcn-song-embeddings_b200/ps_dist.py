@@ -64,6 +64,18 @@ def shard_range(n: int, rank: int, world_size: int):
     return lo, min(n, lo + per)
 
 
+def embed_shard(trainer, rank: int = None, world_size: int = None, chunk: int = 1 << 18, stats=None):
+    """Node-range sharded full-graph inference (BASELINE.json configs[3]): this rank's rows
+    [lo, hi) of the embedding matrix, float32 on the device, computed with no communication (graph, features and
+    neighbourhood table are replicated).  Returns (lo, hi, embeddings)."""
+    rank = trainer.rank if rank is None else rank
+    world_size = trainer.world_size if world_size is None else world_size
+    lo, hi = shard_range(trainer.n, rank, world_size)
+    trainer.model.eval()
+    emb = trainer.model.engine.embed_range(trainer._feats(), lo, hi, chunk=chunk, stats=stats)
+    return lo, hi, emb
+
+
 def max_over_ranks(value: float, device=None) -> float:
     if not (dist.is_initialized() and dist.get_world_size() > 1):
         return value

@@ -352,6 +352,81 @@ class Engine:
         return out[inv]
 
 
+    @torch.no_grad()
+    def embed_range(self, feats: torch.Tensor, lo: int, hi: int, chunk: int = 1 << 18, stats: Optional[dict] = None) -> torch.Tensor:
+        """Full-graph inference for the node range [lo, hi): embeddings float32 [hi-lo, out_dim] on the device.
+        Result-identical to embed(arange(lo, hi)) (per row the same kernels do the same arithmetic) but organised
+        layer by layer over the range's T-hop closure instead of one frontier plan: a dense bool mask per layer marks
+        the nodes whose layer output is needed, Q is applied ONCE per needed input row of a layer, and targets are
+        aggregated in chunks against node-indexed activation tables.  This is the shard a rank owns in node-range
+        sharded inference (BASELINE.json configs[3]); nothing is exchanged between ranks."""
+        m = self.model
+        table = NeighborTable.of(m.nbhds)
+        N, T, L = table.n, m.T, m.n_layers
+        in_dims, dh, do = self._dims()
+        dev = feats.device
+        if not (0 <= lo <= hi <= N):
+            raise IndexError("node range out of bounds")
+        if hi == lo:
+            return torch.empty((0, do), dtype=torch.float32, device=dev)
+
+        def mark_neighbours(mask, idx):
+            for i in range(0, idx.numel(), chunk):
+                mask[table.nodes[idx[i:i + chunk], :T].reshape(-1).long()] = True
+
+        need = [None] * L
+        top = torch.zeros(N, dtype=torch.bool, device=dev)
+        top[lo:hi] = True
+        need[L - 1] = top
+        for l in range(L - 1, 0, -1):
+            nxt = need[l].clone()
+            mark_neighbours(nxt, need[l].nonzero().squeeze(1))
+            need[l - 1] = nxt
+        h_prev = feats
+        for l in range(L):
+            conv = m.conv_layers[l]
+            din = in_dims[l]
+            targets = need[l].nonzero().squeeze(1)
+            zmask = torch.zeros(N, dtype=torch.bool, device=dev)
+            mark_neighbours(zmask, targets)
+            zrows = zmask.nonzero().squeeze(1).to(torch.int32)
+            zpos = (torch.cumsum(zmask, 0, dtype=torch.int32) - 1)
+            del zmask
+            nz = zrows.numel()
+            z = torch.empty((nz, dh), dtype=torch.float32, device=dev)
+            nat.gemm(h_prev, conv.Q.weight, z, nz, dh, din, p_rows=zrows, bias=conv.Q.bias, act=1, tag=f"gemm_q_fwd_l{l}")
+            last = l == L - 1
+            h = torch.empty((hi - lo, do) if last else (N, do), dtype=torch.float32, device=dev)
+            for i in range(0, targets.numel(), chunk):
+                c = targets[i:i + chunk]
+                n = c.numel()
+                nbz = zpos[table.nodes[c, :T].reshape(-1).long()].view(n, T).contiguous()
+                w = table.w[c, :T].contiguous()
+                cat = torch.empty((n, din + dh), dtype=torch.float32, device=dev)
+                inv = torch.empty((n,), dtype=torch.float32, device=dev)
+                nat.aggregate_fwd(h_prev, c.to(torch.int32), din, z, nbz, w, dh, cat, inv, tag=f"aggregate_fwd_l{l}")
+                out = torch.empty((n, do), dtype=torch.float32, device=dev)
+                if do <= 128:
+                    nat.gemm(cat, conv.W.weight, out, n, do, din + dh, bias=conv.W.bias, act=1, l2norm=True, tag=f"gemm_w_fwd_l{l}")
+                else:
+                    nat.gemm(cat, conv.W.weight, out, n, do, din + dh, bias=conv.W.bias, act=1)
+                    nat.l2norm_rows(out, torch.empty((n,), dtype=torch.float32, device=dev))
+                if last:
+                    h[c - lo] = out
+                else:
+                    h[c] = out
+            if stats is not None:
+                stats[f"layer{l}"] = {"targets": int(targets.numel()), "z_rows": int(nz)}
+            del z, zpos, zrows
+            h_prev = h
+        n_top = hi - lo
+        a1 = torch.empty((n_top, do), dtype=torch.float32, device=dev)
+        nat.gemm(h_prev, m.G1.weight, a1, n_top, do, do, bias=m.G1.bias, act=1)
+        out = torch.empty((n_top, do), dtype=torch.float32, device=dev)
+        nat.gemm(a1, m.G2.weight, out, n_top, do, do)
+        return out
+
+
 class PinSageFunction(torch.autograd.Function):
     """Autograd bridge so that `model(features, nodeset)` composes with any torch loss, as
     the reference's nn.Module does.  The backward applies the reference's duplicate-node

@@ -36,15 +36,21 @@ def bipartite_csr(n_tracks: int, n_cols: int, n_edges: int, seed: int = 1234, de
         track = torch.cat([track, miss])
         col = torch.cat([col, torch.randint(0, n_cols, (miss.numel(),), generator=gen, device=device)])
     key = torch.unique(col * n_tracks + track)
-    col, track = key // n_tracks, key % n_tracks
+    del col, track, ut
     e = key.numel()
-    src = torch.cat([track, col + n_tracks])
-    dst = torch.cat([col + n_tracks, track])
-    order = torch.argsort(src, stable=True)
+    # CSR halves built separately (a stable argsort over the 2E directed entries needs several times the memory):
+    # collection rows list their tracks in ascending order (the order of `key`), track rows their collections.
+    col_deg = torch.bincount(key // n_tracks, minlength=n_cols)
+    col_rows = (key % n_tracks).to(torch.int32)
+    key2 = torch.sort((key % n_tracks) * n_cols + key // n_tracks).values
+    del key
+    track_deg = torch.bincount(key2 // n_cols, minlength=n_tracks)
+    track_rows = (key2 % n_cols + n_tracks).to(torch.int32)
+    del key2
     n = n_tracks + n_cols
     indptr = torch.zeros(n + 1, dtype=torch.int64, device=device)
-    indptr[1:] = torch.cumsum(torch.bincount(src, minlength=n), 0)
-    return indptr, dst[order].to(torch.int32), e
+    indptr[1:] = torch.cumsum(torch.cat([track_deg, col_deg]), 0)
+    return indptr, torch.cat([track_rows, col_rows]), e
 
 
 def make_graph(n_tracks, n_cols, n_edges, seed=1234, device="cpu", **kw) -> PSGraph:
@@ -60,7 +66,8 @@ def features(n_tracks, dim, seed=1, device="cpu"):
     (spotify_graph.py:77-79)."""
     gen = torch.Generator(device=device).manual_seed(seed)
     x = torch.randn((n_tracks, dim), generator=gen, device=device, dtype=torch.float32)
-    return (x - x.mean(0)) / (x.std(0, unbiased=True) + 1e-12)
+    mean, std = x.mean(0), x.std(0, unbiased=True)
+    return x.sub_(mean).div_(std + 1e-12)  # in place: the cfg4 table is 41 GB
 
 
 def cooccurrence_positives(indptr, indices, n_tracks, n_pairs, seed=2):

@@ -269,8 +269,70 @@ def gen_dataset():
     print("dataset", features.shape, pos.shape, train.shape, test.shape)
 
 
+def gen_eval_parity():
+    """BASELINE.json configs[1] stand-in (the real dataset_final_intersect is not in the checkout): the REFERENCE
+    end to end on a small synthetic dataset in its own on-disk schema -- SpotifyGraph loader, 70/30 split,
+    precompute_neighborhoods_topt (its mt19937 walker), PinSage.train_batch for 120 steps from a seeded state on
+    batches drawn by its own sample_batch, embed, knn_from_emb, hit_rate / mrr (eval.py) -- plus two more training
+    seeds to measure the reference's own run-to-run noise.  The GPU test replays the same state / neighbourhoods /
+    batches through the drop-in trainer and compares losses, embeddings and metrics."""
+    import ps_synth
+    from spotify_graph import SpotifyGraph as RefSpotifyGraph  # the reference
+    import eval as ref_eval
+    import baselines as ref_bl
+    n_tracks, n_cols, n_steps, B, K = 600, 90, 120, 128, 50
+    cwd = os.getcwd()
+    with tempfile.TemporaryDirectory() as tmp:
+        ps_synth.write_dataset(tmp, n_tracks, n_cols, 7000, 128, 6000, seed=31)
+        ds = RefSpotifyGraph(tmp, os.path.join(tmp, "features_openl3"))
+        g, track_ids, col_ids, features = ds.to_dgl_graph()
+        train_pos, test_pos = ds.load_positives_split(os.path.join(tmp, "positives_lfm.json"))
+        os.chdir(tmp); os.mkdir("runs")
+        torch.manual_seed(5)
+        trainer = ref_pst.PinSage(g, n_tracks, features, train_pos, log=False, load_save=False)  # runs the reference walker
+        os.chdir(cwd)
+        w, nodes = trainer.nbhds
+
+        def run(seed, keep):
+            params = oracle.make_params(2, (128, 512, 128), np.random.RandomState(seed))
+            trainer.model.load_state_dict(params)
+            trainer.optimizer = torch.optim.Adam(trainer.model.parameters(), lr=trainer.lr)
+            torch.manual_seed(seed)
+            batches, losses = [], []
+            for _ in range(n_steps):
+                batch, _ = ref_pst.sample_batch(trainer.all_ids, train_pos, B, trainer.nbhds, hard_negatives=False)
+                loss, _, _ = trainer.train_batch(batch)
+                batches.append(batch.numpy().copy()); losses.append(float(loss))
+            emb = trainer.embed(torch.arange(n_tracks)).detach()
+            knn_w, knn_n = ref_bl.knn_from_emb(emb, torch.arange(n_tracks), K, None)
+            m = {"hr10": ref_eval.hit_rate(knn_n, test_pos, 10), "hr50": ref_eval.hit_rate(knn_n, test_pos, 50),
+                 "mrr": ref_eval.mrr(knn_n, test_pos, K)}
+            return (np.stack(batches), np.array(losses), emb.numpy(), knn_n.numpy(), m) if keep else m
+
+        batches, losses, emb, knn_n, m0 = run(41, True)
+        # the reference is not bit-reproducible (threaded reductions) and 120 Adam steps amplify rounding noise on
+        # near-zero gradient components: rerun the same seed to measure how far it drifts from itself
+        _, losses2, emb2, knn2, _ = run(41, True)
+        emb_rerun_rel = float(np.linalg.norm(emb2 - emb) / np.linalg.norm(emb))
+        knn_rerun_agree = float(np.mean([len(set(a) & set(b)) / K for a, b in zip(knn_n.tolist(), knn2.tolist())]))
+        loss_rerun_abs = float(np.abs(losses2 - losses).max())
+        others = [run(s, False) for s in (42, 43)]
+    allm = [m0] + others
+    out = {"n_tracks": np.int64(n_tracks), "features": features.numpy(), "train_pos": train_pos.numpy(), "test_pos": test_pos.numpy(),
+           "nb_counts": np.rint(w.numpy() * 500).astype(np.uint16), "nb_nodes": nodes.numpy().astype(np.int32),
+           "param_seed": np.int64(41), "batches": batches.astype(np.int16), "losses": losses, "emb": emb, "knn_n": knn_n.astype(np.int16),
+           "K": np.int64(K), "emb_rerun_rel": np.float64(emb_rerun_rel), "knn_rerun_agree": np.float64(knn_rerun_agree),
+           "loss_rerun_abs": np.float64(loss_rerun_abs)}
+    for k in ("hr10", "hr50", "mrr"):
+        out[k] = np.float64(m0[k]); out[k + "_seeds"] = np.array([float(m[k]) for m in allm])
+    assert np.array_equal(out["nb_counts"].astype(np.float64) / 500.0, w.numpy())
+    np.savez_compressed(os.path.join(OUT, "eval_parity.npz"), **out)
+    print("eval_parity", {k: out[k + "_seeds"] for k in ("hr10", "hr50", "mrr")}, "loss", losses[0], losses[-1],
+          "self-rerun: emb rel", emb_rerun_rel, "knn agree", knn_rerun_agree, "loss abs", loss_rerun_abs)
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["walk_topt", "walk_dist", "frontier", "model", "train_steps", "loss", "metrics_knn", "dataset"]
+    which = sys.argv[1:] or ["walk_topt", "walk_dist", "frontier", "model", "train_steps", "loss", "metrics_knn", "dataset", "eval_parity"]
     if "walk_topt" in which: gen_walk_topt()
     if "walk_dist" in which: gen_walk_dist()
     if "frontier" in which: gen_frontier()
@@ -282,3 +344,4 @@ if __name__ == "__main__":
     if "loss" in which: gen_loss()
     if "metrics_knn" in which: gen_metrics_knn()
     if "dataset" in which: gen_dataset()
+    if "eval_parity" in which: gen_eval_parity()

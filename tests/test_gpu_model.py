@@ -166,3 +166,25 @@ def test_state_dict_roundtrip_with_reference_keys(golden):
     assert list(sd) == list(params)
     for k in params:
         assert torch.equal(sd[k].cpu(), params[k])
+
+
+def test_embed_range_equals_frontier_embed():
+    """Layer-wise node-range inference (Engine.embed_range, the shard of BASELINE.json configs[3]) gives the same
+    embeddings as the per-batch frontier path (PinSage.embed), for 2 and 3 layers, ragged ranges and tiny chunks."""
+    import ps_synth
+    import pinsage_model as psm
+    from oracle import oracle
+    n_tracks = 900
+    g = ps_synth.make_graph(n_tracks, 120, 9000, seed=5)
+    feats = ps_synth.features(n_tracks, 64, seed=6).cuda()
+    nb = psm.sample_neighborhood_topt(g, n_tracks, torch.arange(n_tracks), 300, 0.85, 12, seed=3)
+    for L, T, dims in ((2, 5, (64, 96, 32)), (3, 4, (64, 48, 64))):
+        model = psm.PinSageModel(g, n_tracks, L, dims, 300, 0.85, T, nb)
+        model.load_state_dict(oracle.make_params(L, dims, np.random.RandomState(L)))
+        want = model.engine.embed(feats, torch.arange(n_tracks, device="cuda"))
+        for lo, hi, chunk in ((0, n_tracks, 1 << 18), (0, n_tracks, 97), (123, 457, 64), (899, 900, 8), (10, 10, 8)):
+            st = {}
+            got = model.engine.embed_range(feats, lo, hi, chunk=chunk, stats=st)
+            assert got.shape == (hi - lo, dims[2])
+            if hi > lo:
+                assert torch.allclose(got, want[lo:hi], rtol=1e-5, atol=1e-6), float((got - want[lo:hi]).abs().max())
