@@ -123,6 +123,12 @@ walk_topt_kernel(const PtrT* __restrict__ indptr, const int32_t* __restrict__ in
         }
         __syncwarp();
 
+        PtrT sbeg = 0;   // the source's own row bounds: 85 % of the steps start there
+        uint32_t sdeg = 0;
+        if (!kFromTrace) {
+            sbeg = __ldg(indptr + src);
+            sdeg = static_cast<uint32_t>(__ldg(indptr + src + 1) - sbeg);
+        }
         uint32_t carry_item = src;  // where step 0 of the next pass starts from
 
         for (int base = 0; base < n_hops; base += 32 * kChunks) {
@@ -159,6 +165,10 @@ walk_topt_kernel(const PtrT* __restrict__ indptr, const int32_t* __restrict__ in
                 if (lane == 0) item[0] = carry_item;
                 for (int k = 0; k <= maxpos; ++k) {
                     // round k advances the steps at position k from their predecessor's item
+                    // the loads of the kChunks independent steps of a lane are issued stage by stage so they overlap
+                    uint32_t cur[kChunks], deg[kChunks];
+                    PtrT beg[kChunks];
+                    bool act[kChunks];
 #pragma unroll
                     for (int c = 0; c < kChunks; ++c) {
                         uint32_t prev = __shfl_up_sync(0xffffffffu, item[c], 1);
@@ -166,12 +176,32 @@ walk_topt_kernel(const PtrT* __restrict__ indptr, const int32_t* __restrict__ in
                             const uint32_t tail = __shfl_sync(0xffffffffu, item[c - 1], 31);
                             if (lane == 0) prev = tail;
                         }
-                        // a real branch: a chunk without a step at position k (most chunks once k >= 2) costs nothing
-                        if (valid[c] && pos[c] == k) {
-                            const uint32_t cur = k == 0 ? item[c] : prev;
-                            const uint32_t col = hop(indptr, indices, cur, x0[c]);
-                            item[c] = hop(indptr, indices, col, x1[c]);
+                        act[c] = valid[c] && pos[c] == k;
+                        cur[c] = k == 0 ? item[c] : prev;
+                    }
+#pragma unroll
+                    for (int c = 0; c < kChunks; ++c) {
+                        beg[c] = sbeg; deg[c] = sdeg;  // 85 % of the steps start at the source: its row bounds are in registers
+                        if (act[c] && cur[c] != src) {
+                            beg[c] = __ldg(indptr + cur[c]);
+                            deg[c] = static_cast<uint32_t>(__ldg(indptr + cur[c] + 1) - beg[c]);
                         }
+                    }
+#pragma unroll
+                    for (int c = 0; c < kChunks; ++c)
+                        if (act[c] && deg[c] != 0) cur[c] = static_cast<uint32_t>(__ldg(indices + beg[c] + __umulhi(x0[c], deg[c])));
+#pragma unroll
+                    for (int c = 0; c < kChunks; ++c) {
+                        deg[c] = 0;
+                        if (act[c]) {
+                            beg[c] = __ldg(indptr + cur[c]);
+                            deg[c] = static_cast<uint32_t>(__ldg(indptr + cur[c] + 1) - beg[c]);
+                        }
+                    }
+#pragma unroll
+                    for (int c = 0; c < kChunks; ++c) {
+                        if (act[c] && deg[c] != 0) cur[c] = static_cast<uint32_t>(__ldg(indices + beg[c] + __umulhi(x1[c], deg[c])));
+                        if (act[c]) item[c] = cur[c];
                     }
                 }
                 carry_item = (rm[kChunks - 1] >> 31) ? src : __shfl_sync(0xffffffffu, item[kChunks - 1], 31);

@@ -64,15 +64,33 @@ def shard_range(n: int, rank: int, world_size: int):
     return lo, min(n, lo + per)
 
 
-def embed_shard(trainer, rank: int = None, world_size: int = None, chunk: int = 1 << 18, stats=None):
+def embed_shard(trainer, rank: int = None, world_size: int = None, chunk: int = 1 << 18, stats=None, exchange: bool = False):
     """Node-range sharded full-graph inference (BASELINE.json configs[3]): this rank's rows
-    [lo, hi) of the embedding matrix, float32 on the device, computed with no communication (graph, features and
-    neighbourhood table are replicated).  Returns (lo, hi, embeddings)."""
+    [lo, hi) of the embedding matrix, float32 on the device.  Graph, features and neighbourhood table are replicated.
+    exchange=False (the contract): no communication, every rank recomputes the T-hop closure of its range.
+    exchange=True: every rank computes each layer for its own rows only and the layer outputs are all-gathered
+    (L-1 all-gathers of [N, out_dim] fp32 over NCCL / NVLink): same result, 1/world of the work per rank.
+    Returns (lo, hi, embeddings)."""
     rank = trainer.rank if rank is None else rank
     world_size = trainer.world_size if world_size is None else world_size
     lo, hi = shard_range(trainer.n, rank, world_size)
     trainer.model.eval()
-    emb = trainer.model.engine.embed_range(trainer._feats(), lo, hi, chunk=chunk, stats=stats)
+    gather = None
+    if exchange and world_size > 1:
+        per = -(-trainer.n // world_size)
+
+        def gather(table, lo_, hi_):
+            # equal-sized padded shards so one all_gather_into_tensor moves everything
+            n, d = table.shape
+            if per * world_size == n:  # even shards: gather straight into the table
+                dist.all_gather_into_tensor(table, table[lo_:hi_].clone())
+                return
+            mine = torch.zeros((per, d), dtype=table.dtype, device=table.device)
+            mine[: hi_ - lo_] = table[lo_:hi_]
+            full = torch.empty((per * world_size, d), dtype=table.dtype, device=table.device)
+            dist.all_gather_into_tensor(full, mine)
+            table.copy_(full[:n])
+    emb = trainer.model.engine.embed_range(trainer._feats(), lo, hi, chunk=chunk, stats=stats, gather_layer=gather)
     return lo, hi, emb
 
 

@@ -353,13 +353,19 @@ class Engine:
 
 
     @torch.no_grad()
-    def embed_range(self, feats: torch.Tensor, lo: int, hi: int, chunk: int = 1 << 18, stats: Optional[dict] = None) -> torch.Tensor:
+    def embed_range(self, feats: torch.Tensor, lo: int, hi: int, chunk: int = 1 << 18, stats: Optional[dict] = None,
+                    gather_layer=None) -> torch.Tensor:
         """Full-graph inference for the node range [lo, hi): embeddings float32 [hi-lo, out_dim] on the device.
         Result-identical to embed(arange(lo, hi)) (per row the same kernels do the same arithmetic) but organised
         layer by layer over the range's T-hop closure instead of one frontier plan: a dense bool mask per layer marks
         the nodes whose layer output is needed, Q is applied ONCE per needed input row of a layer, and targets are
         aggregated in chunks against node-indexed activation tables.  This is the shard a rank owns in node-range
-        sharded inference (BASELINE.json configs[3]); nothing is exchanged between ranks."""
+        sharded inference (BASELINE.json configs[3]); nothing is exchanged between ranks.
+
+        gather_layer (optional): a callable(table [N, out_dim], lo, hi) that fills the rows outside [lo, hi) of a
+        layer's node-indexed output table from the other ranks (an all-gather).  With it every rank computes every
+        layer for ITS range only (no closure, 1/world of the work) and the result is still identical: the closure
+        rows it would have recomputed arrive from their owners."""
         m = self.model
         table = NeighborTable.of(m.nbhds)
         N, T, L = table.n, m.T, m.n_layers
@@ -379,6 +385,9 @@ class Engine:
         top[lo:hi] = True
         need[L - 1] = top
         for l in range(L - 1, 0, -1):
+            if gather_layer is not None:
+                need[l - 1] = top  # owners compute, the exchange delivers the rest
+                continue
             nxt = need[l].clone()
             mark_neighbours(nxt, need[l].nonzero().squeeze(1))
             need[l - 1] = nxt
@@ -418,6 +427,8 @@ class Engine:
             if stats is not None:
                 stats[f"layer{l}"] = {"targets": int(targets.numel()), "z_rows": int(nz)}
             del z, zpos, zrows
+            if gather_layer is not None and not last:
+                gather_layer(h, lo, hi)
             h_prev = h
         n_top = hi - lo
         a1 = torch.empty((n_top, do), dtype=torch.float32, device=dev)
