@@ -263,6 +263,20 @@ __device__ __forceinline__ Work decode_work(const TcArgs& a, int64_t w, int bn) 
     return {m_idx * BM, n_idx * static_cast<int64_t>(bn), static_cast<int>(b), static_cast<int>(e - b)};
 }
 
+// Load-side cursor of the MN-major x MN-major (weight-gradient) producers: the operand views of the k-block whose
+// asynchronous copies are issued next, one k-block ahead of the split pass, across tile boundaries.
+template <typename OpA, typename OpB>
+struct LoadCursor {
+    OpA a; OpB b;
+    int64_t w; int kb; int nkb; int64_t k0; bool valid;
+};
+
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint32_t src_bytes) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
 // Thread roles (20 warps): 0-7 accumulate + epilogue, 8-15 producers, 16 MMA issue (17-19 only give their
 // registers away: setmaxnreg works on whole warpgroups).  Persistent: every role walks the same list of work
 // items (blockIdx.x, + gridDim.x, ...), so the producers and the MMA warp run ahead into the next tile while
@@ -394,6 +408,102 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(TcArgs a) {
                 if (++stage == STAGES) { stage = 0; phase ^= 1; }
 #pragma unroll
                 for (int j = 0; j < NJ; ++j) cur[j] = nxt[j];
+            }
+        }
+    } else if (warp >= 8 && !PK && !QK) {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+        // ------------------------------------------------ producers, MN-major x MN-major (weight gradients)
+        // The tensor core reads an fp32 word as tf32 by ignoring its low 13 mantissa bits, so the RAW operand is its
+        // own "hi" tile: cp.async (LDGSTS, no registers held) copies the k-block straight into the hi tiles of the
+        // stage, one k-block ahead of use, and the split pass only reads it back from shared memory, computes
+        // lo = x - hi(x) and writes the lo tiles.  Loading through registers kept 8 x 16 B per thread in flight and
+        // exposed ~4 memory latencies per k-block (index -> row, twice); this keeps the whole next k-block in flight.
+        const int t = tid - 8 * 32;
+        using OpA = Operand<false, BM, true>;
+        using OpB = Operand<false, BN, false>;
+        LoadCursor<OpA, OpB> lc;
+        lc.w = blockIdx.x; lc.kb = 0;
+        lc.valid = lc.w < total_work;
+        {
+            const Work wk = decode_work(a, lc.valid ? lc.w : 0, BN);
+            lc.nkb = wk.num_kb;
+            lc.k0 = static_cast<int64_t>(wk.kb_begin) * BK;
+            lc.a.init(a.P, a.ldp, a.p_rows, wk.m0, a.M, t);
+            lc.b.init(a.Q, a.ldq, a.q_rows, wk.n0, a.N, t);
+        }
+        const uint32_t offa = lc.a.off0, offb = lc.b.off0;  // shared-memory offsets depend on the thread only
+        const uint32_t smem0 = smem_u32(smem);
+        auto issue = [&](int stage_) {  // asynchronous copies of the cursor's k-block into the hi tiles of stage_
+            const uint32_t sa = smem0 + stage_ * STAGE_BYTES;
+#pragma unroll
+            for (int j = 0; j < OpA::NJ; ++j) {
+                const int64_t k = lc.k0 + lc.a.kq + OpA::RPP * j;
+                const bool ok = k < a.K;
+                const int64_t row = ok ? (lc.a.rows ? static_cast<int64_t>(__ldg(lc.a.rows + k)) : k) : 0;
+                cp_async16(sa + offa + j * OpA::kStep, lc.a.base[0] + row * lc.a.ld, ok ? 16u : 0u);
+            }
+#pragma unroll
+            for (int j = 0; j < OpB::NJ; ++j) {
+                const int64_t k = lc.k0 + lc.b.kq + OpB::RPP * j;
+                const bool ok = k < a.K;
+                const int64_t row = ok ? (lc.b.rows ? static_cast<int64_t>(__ldg(lc.b.rows + k)) : k) : 0;
+                cp_async16(sa + 2 * A_BYTES + offb + j * OpB::kStep, lc.b.base[0] + row * lc.b.ld, ok ? 16u : 0u);
+            }
+            cp_async_commit();
+        };
+        auto advance = [&]() {
+            if (++lc.kb == lc.nkb) {
+                lc.w += gridDim.x; lc.kb = 0;
+                lc.valid = lc.w < total_work;
+                if (lc.valid) {
+                    const Work wk = decode_work(a, lc.w, BN);
+                    lc.nkb = wk.num_kb;
+                    lc.k0 = static_cast<int64_t>(wk.kb_begin) * BK;
+                    lc.a.init(a.P, a.ldp, a.p_rows, wk.m0, a.M, t);
+                    lc.b.init(a.Q, a.ldq, a.q_rows, wk.n0, a.N, t);
+                }
+            } else {
+                lc.k0 += BK;
+            }
+        };
+        int stage = 0; uint32_t phase = 0;
+        if (lc.valid) {  // prologue: the first k-block (its stage is free)
+            issue(0);
+            advance();
+        }
+        for (int64_t w = blockIdx.x; w < total_work; w += gridDim.x) {
+            const Work wk = decode_work(a, w, BN);
+            for (int kb = 0; kb < wk.num_kb; ++kb) {
+                // split pass of the current k-block: its copies were issued one iteration ago
+                cp_async_wait_all();
+                uint8_t* st = smem + stage * STAGE_BYTES;
+#pragma unroll
+                for (int j = 0; j < OpA::NJ; ++j) {
+                    float4* hp = reinterpret_cast<float4*>(st + offa + j * OpA::kStep);
+                    const float4 v = *hp;
+                    float4 l;
+                    l.x = v.x - __uint_as_float(__float_as_uint(v.x) & kHiMask); l.y = v.y - __uint_as_float(__float_as_uint(v.y) & kHiMask);
+                    l.z = v.z - __uint_as_float(__float_as_uint(v.z) & kHiMask); l.w = v.w - __uint_as_float(__float_as_uint(v.w) & kHiMask);
+                    *reinterpret_cast<float4*>(st + A_BYTES + offa + j * OpA::kStep) = l;
+                }
+#pragma unroll
+                for (int j = 0; j < OpB::NJ; ++j) {
+                    float4* hp = reinterpret_cast<float4*>(st + 2 * A_BYTES + offb + j * OpB::kStep);
+                    const float4 v = *hp;
+                    float4 l;
+                    l.x = v.x - __uint_as_float(__float_as_uint(v.x) & kHiMask); l.y = v.y - __uint_as_float(__float_as_uint(v.y) & kHiMask);
+                    l.z = v.z - __uint_as_float(__float_as_uint(v.z) & kHiMask); l.w = v.w - __uint_as_float(__float_as_uint(v.w) & kHiMask);
+                    *reinterpret_cast<float4*>(st + 2 * A_BYTES + B_BYTES + offb + j * OpB::kStep) = l;
+                }
+                fence_proxy_async();
+                mbar_arrive(full0 + 8 * stage);
+                if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                // copies of the next k-block into the stage that follows (free once the MMAs that read it are done)
+                if (lc.valid) {
+                    mbar_wait(empty0 + 8 * stage, phase ^ 1);
+                    issue(stage);
+                    advance();
+                }
             }
         }
     } else if (warp >= 8) {

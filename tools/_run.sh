@@ -1,4 +1,4 @@
-timeout 600 python bench.py --steps 20 --warmup 3 > gpurun_out/bench15.log 2>&1; tail -1 gpurun_out/bench15.log | cut -c1-250
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --nvtx --nvtx-include "ps_step/" -c 600 --csv --log-file gpurun_out/launches_r1g.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_launch3.log 2>&1
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:"aggregate_bwd_kernel|aggregate_fwd_kernel" -s 8 -c 4 -f -o gpurun_out/prof_agg2 python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_agg2.log 2>&1; tail -1 gpurun_out/ncu_agg2.log
-timeout 300 ncu --set full --clock-control none --import-source on -k regex:walk_topt -s 1 -c 1 -f -o gpurun_out/prof_walk4 python tools/walker_microbench.py > gpurun_out/ncu_walk4.log 2>&1; tail -1 gpurun_out/ncu_walk4.log
+timeout 900 python -m pytest tests -m gpu -q > gpurun_out/test12.log 2>&1; echo "pytest rc=$?" >> gpurun_out/test12.log
+tail -3 gpurun_out/test12.log
+timeout 600 python bench.py --steps 20 --warmup 3 --no-cpu-baseline > gpurun_out/bench16.log 2>&1; tail -1 gpurun_out/bench16.log | python -c "
+import json,sys; d=json.loads(sys.stdin.read()); print(d['value'], d['ms_per_step'], d['e2e']['ms_per_step'], d['host_ms_per_step'], d['walk']['ms']); print({k:v['ms_per_step'] for k,v in d['roofline']['all'].items()})"
