@@ -276,15 +276,17 @@ def run_ours(args, wl):
     ps_dist.attach(trainer, rank, world)
     nbhds_cpu = trainer.nbhds
 
-    pending = [trainer.prefetch()]  # batch i+1 is sampled + planned on a side stream while step i runs
+    from collections import deque
+    # batches i+1 and i+2 are sampled + planned by a worker thread on a side stream while step i runs (PinSage.train does the same)
+    pending = deque([trainer.prefetch_async(), trainer.prefetch_async()])
 
     host = {"train": 0.0, "prefetch": 0.0}
 
     def device_step():
         h0 = time.perf_counter()
-        out = trainer.train_batch(pending[0])
+        out = trainer.train_batch(pending.popleft())
         h1 = time.perf_counter()
-        pending[0] = trainer.prefetch()
+        pending.append(trainer.prefetch_async())
         host["train"] += h1 - h0; host["prefetch"] += time.perf_counter() - h1
         return out
 
@@ -323,23 +325,20 @@ def run_ours(args, wl):
     # ---- e2e: the same public call with HOST batches (pinned -> H2D -> step -> D2H of the loss) ----
     pos_cpu = positives.cpu()
     ids_cpu = torch.arange(N)
-    pinned = torch.empty((B, 3), dtype=torch.int64).pin_memory()
-
-    pinned2 = torch.empty((B, 3), dtype=torch.int64).pin_memory()
-    bufs = [pinned, pinned2]
-    e2e_state = {"i": 0, "pending": None}
+    bufs = [torch.empty((B, 3), dtype=torch.int64).pin_memory() for _ in range(4)]
+    e2e_state = {"i": 0, "pending": deque()}
 
     def e2e_prefetch():
-        buf = bufs[e2e_state["i"] & 1]; e2e_state["i"] += 1
+        buf = bufs[e2e_state["i"] % len(bufs)]; e2e_state["i"] += 1   # 4 pinned buffers: at most 3 batches are alive at once
         batch, _ = pst.sample_batch(ids_cpu, pos_cpu, B, nbhds_cpu, hard_negatives=False)  # host sampling
         buf.copy_(batch)
-        return trainer.prefetch(buf)  # H2D of the pinned batch + planning, on the side stream
+        return trainer.prefetch_async(buf)  # H2D of the pinned batch + planning, worker thread / side stream
 
     def e2e_step():
-        if e2e_state["pending"] is None:
-            e2e_state["pending"] = e2e_prefetch()
-        out = trainer.train_batch(e2e_state["pending"])
-        e2e_state["pending"] = e2e_prefetch()
+        while len(e2e_state["pending"]) < 2:
+            e2e_state["pending"].append(e2e_prefetch())
+        out = trainer.train_batch(e2e_state["pending"].popleft())
+        e2e_state["pending"].append(e2e_prefetch())
         return float(out[0])  # D2H read of the step's result
 
     for _ in range(args.warmup):

@@ -26,7 +26,7 @@ int ps_gemm_tc_launch(const float* P, int64_t ldp, int p_kmajor, const int32_t* 
                       const float* Q, int64_t ldq, int q_kmajor, const int32_t* q_rows,
                       float* C, int64_t ldc, int64_t M, int64_t N, int64_t K,
                       const float* bias, int act, int l2norm, float* norm_out, int accumulate, int splits,
-                      cudaStream_t stream);
+                      uint32_t* mask, int64_t ldm, cudaStream_t stream);
 
 static int g_gemm_backend = 0;  // 0 = tcgen05 3xTF32 where the shape allows, 1 = CUDA-core fp32 only
 
@@ -49,11 +49,26 @@ extern "C" int ps_gemm(const float* P, int64_t ldp, int p_kmajor, const int32_t*
                        float* C, int64_t ldc, int64_t M, int64_t N, int64_t K,
                        const float* bias, int act, int l2norm, float* norm_out, int accumulate, int splits,
                        ps_stream_t stream) {
+    return ps_gemm_ex(P, ldp, p_kmajor, p_rows, Q, ldq, q_kmajor, q_rows, C, ldc, M, N, K, bias, act, l2norm, norm_out, accumulate, splits,
+                      nullptr, 0, stream);
+}
+
+extern "C" int ps_gemm_mask_supported(int64_t M, int64_t N, int64_t K) {
+    return g_gemm_backend == 0 && M > 0 && N >= 64 && N % 32 == 0 && K >= 32 && K % 4 == 0 && K <= 8192;
+}
+
+extern "C" int ps_gemm_ex(const float* P, int64_t ldp, int p_kmajor, const int32_t* p_rows,
+                          const float* Q, int64_t ldq, int q_kmajor, const int32_t* q_rows,
+                          float* C, int64_t ldc, int64_t M, int64_t N, int64_t K,
+                          const float* bias, int act, int l2norm, float* norm_out, int accumulate, int splits,
+                          uint32_t* mask, int64_t ld_mask, ps_stream_t stream) {
     if (g_gemm_backend == 0) {
         const int rc = ps_gemm_tc_launch(P, ldp, p_kmajor, p_rows, Q, ldq, q_kmajor, q_rows, C, ldc, M, N, K, bias, act, l2norm,
-                                         norm_out, accumulate, splits, static_cast<cudaStream_t>(stream));
+                                         norm_out, accumulate, splits, mask, ld_mask, static_cast<cudaStream_t>(stream));
         if (rc != PS_ERR_UNSUPPORTED) return rc;
     }
+    if (mask != nullptr)
+        return ps_fail(PS_ERR_UNSUPPORTED, "ps_gemm_ex: the sign-mask epilogue needs the tensor-core path (check ps_gemm_mask_supported)");
     return ps_gemm_simt_launch(P, ldp, p_kmajor, p_rows, Q, ldq, q_kmajor, q_rows, C, ldc, M, N, K, bias, act, l2norm,
                                norm_out, accumulate, splits, static_cast<cudaStream_t>(stream));
 }

@@ -93,7 +93,7 @@ aggregate_bwd_kernel(const float* __restrict__ dcat, int64_t ldcat, int col_off,
                      const int32_t* __restrict__ pair_q, const float* __restrict__ nbw,
                      const float* __restrict__ inv_wsum, int T,
                      float* __restrict__ z, int64_t ldz, int64_t n_zrows, float* __restrict__ partial,
-                     const int32_t* __restrict__ chunk_row) {
+                     const int32_t* __restrict__ chunk_row, int apply_leaky) {
     const int lane = threadIdx.x & 31;
     const int64_t chunk = static_cast<int64_t>(blockIdx.x) * kWarps + (threadIdx.x >> 5);
     if (chunk >= __ldg(chunk_off + n_zrows)) return;
@@ -162,10 +162,14 @@ aggregate_bwd_kernel(const float* __restrict__ dcat, int64_t ldcat, int col_off,
         for (int c = 0; c < CH; ++c) {
             const int col = (c * 32 + lane) * 4;
             if (col < dh) {
-                const float4 y = __ldcs(reinterpret_cast<const float4*>(zr + col));
-                __stcs(reinterpret_cast<float4*>(zr + col),
-                       make_float4(acc[c].x * ps_leaky_grad_from_out(y.x), acc[c].y * ps_leaky_grad_from_out(y.y),
-                                   acc[c].z * ps_leaky_grad_from_out(y.z), acc[c].w * ps_leaky_grad_from_out(y.w)));
+                if (apply_leaky) {
+                    const float4 y = __ldcs(reinterpret_cast<const float4*>(zr + col));
+                    __stcs(reinterpret_cast<float4*>(zr + col),
+                           make_float4(acc[c].x * ps_leaky_grad_from_out(y.x), acc[c].y * ps_leaky_grad_from_out(y.y),
+                                       acc[c].z * ps_leaky_grad_from_out(y.z), acc[c].w * ps_leaky_grad_from_out(y.w)));
+                } else {
+                    *reinterpret_cast<float4*>(zr + col) = acc[c];
+                }
             }
         }
     } else {
@@ -183,7 +187,7 @@ aggregate_bwd_kernel(const float* __restrict__ dcat, int64_t ldcat, int col_off,
 template <int CH>
 __global__ void __launch_bounds__(kWarps * 32)
 aggregate_bwd_reduce_kernel(const int32_t* __restrict__ chunk_off, const float* __restrict__ partial, int dh,
-                            float* __restrict__ z, int64_t ldz, int64_t n_zrows) {
+                            float* __restrict__ z, int64_t ldz, int64_t n_zrows, int apply_leaky) {
     const int lane = threadIdx.x & 31;
     const int64_t u = static_cast<int64_t>(blockIdx.x) * kWarps + (threadIdx.x >> 5);
     if (u >= n_zrows) return;
@@ -208,10 +212,14 @@ aggregate_bwd_reduce_kernel(const int32_t* __restrict__ chunk_off, const float* 
     for (int c = 0; c < CH; ++c) {
         const int col = (c * 32 + lane) * 4;
         if (col < dh) {
-            const float4 y = *reinterpret_cast<const float4*>(zr + col);
-            *reinterpret_cast<float4*>(zr + col) =
-                make_float4(acc[c].x * ps_leaky_grad_from_out(y.x), acc[c].y * ps_leaky_grad_from_out(y.y),
-                            acc[c].z * ps_leaky_grad_from_out(y.z), acc[c].w * ps_leaky_grad_from_out(y.w));
+            if (apply_leaky) {
+                const float4 y = *reinterpret_cast<const float4*>(zr + col);
+                *reinterpret_cast<float4*>(zr + col) =
+                    make_float4(acc[c].x * ps_leaky_grad_from_out(y.x), acc[c].y * ps_leaky_grad_from_out(y.y),
+                                acc[c].z * ps_leaky_grad_from_out(y.z), acc[c].w * ps_leaky_grad_from_out(y.w));
+            } else {
+                *reinterpret_cast<float4*>(zr + col) = acc[c];
+            }
         }
     }
 }
@@ -343,7 +351,7 @@ extern "C" int ps_aggregate_bwd(const float* dcat, int64_t ldcat, int col_off, i
                                 const int32_t* chunk_off, int chunk_pairs, int64_t max_chunks,
                                 const int32_t* pair_q, const float* nbw, const float* inv_wsum, int T,
                                 float* z, int64_t ldz, int64_t n_zrows, float* partial_ws, const int32_t* chunk_row,
-                                ps_stream_t stream_) {
+                                int apply_leaky, ps_stream_t stream_) {
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     PS_REQUIRE(dcat && seg_off && chunk_off && pair_q && nbw && inv_wsum && z && partial_ws, "null pointer");
     PS_REQUIRE(dh > 0 && dh % 4 == 0 && col_off % 4 == 0 && ldcat % 4 == 0 && ldz % 4 == 0 && T > 0, "bad shape");
@@ -354,11 +362,11 @@ extern "C" int ps_aggregate_bwd(const float* dcat, int64_t ldcat, int col_off, i
         const unsigned blocks = static_cast<unsigned>(ps_ceil_div(max_chunks, kWarps));
         PS_DISPATCH_CH(dh, (aggregate_bwd_kernel<CH><<<blocks, kWarps * 32, 0, stream>>>(
                                dcat, ldcat, col_off, dh, seg_off, chunk_off, chunk_pairs, pair_q, nbw, inv_wsum, T, z, ldz,
-                               n_zrows, partial_ws, chunk_row)));
+                               n_zrows, partial_ws, chunk_row, apply_leaky)));
         PS_LAUNCH_CHECK();
     }
     const unsigned rblocks = static_cast<unsigned>(ps_ceil_div(n_zrows, kWarps));
-    PS_DISPATCH_CH(dh, (aggregate_bwd_reduce_kernel<CH><<<rblocks, kWarps * 32, 0, stream>>>(chunk_off, partial_ws, dh, z, ldz, n_zrows)));
+    PS_DISPATCH_CH(dh, (aggregate_bwd_reduce_kernel<CH><<<rblocks, kWarps * 32, 0, stream>>>(chunk_off, partial_ws, dh, z, ldz, n_zrows, apply_leaky)));
     PS_LAUNCH_CHECK();
     return PS_OK;
 }

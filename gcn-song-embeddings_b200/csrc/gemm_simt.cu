@@ -148,6 +148,10 @@ __global__ void __launch_bounds__(THREADS, 2) gemm_simt_kernel(GemmArgs a) {
                     if (a.accumulate) {
                         atomicAdd(dst + 0, acc[i][h * 4 + 0]); atomicAdd(dst + 1, acc[i][h * 4 + 1]);
                         atomicAdd(dst + 2, acc[i][h * 4 + 2]); atomicAdd(dst + 3, acc[i][h * 4 + 3]);
+                    } else if (a.act == 2) {  // C holds leaky_relu outputs y: C = acc * leaky'(y)
+                        const float4 y = *reinterpret_cast<const float4*>(dst);
+                        *reinterpret_cast<float4*>(dst) = make_float4(acc[i][h * 4 + 0] * ps_leaky_grad_from_out(y.x), acc[i][h * 4 + 1] * ps_leaky_grad_from_out(y.y),
+                                                                      acc[i][h * 4 + 2] * ps_leaky_grad_from_out(y.z), acc[i][h * 4 + 3] * ps_leaky_grad_from_out(y.w));
                     } else {
                         *reinterpret_cast<float4*>(dst) = make_float4(acc[i][h * 4 + 0], acc[i][h * 4 + 1], acc[i][h * 4 + 2], acc[i][h * 4 + 3]);
                     }
@@ -174,6 +178,7 @@ int ps_gemm_simt_launch(const float* P, int64_t ldp, int p_kmajor, const int32_t
     PS_REQUIRE(!l2norm || N <= BN, "l2norm epilogue needs N <= 128");
     PS_REQUIRE(splits >= 1, "splits must be >= 1");
     PS_REQUIRE(!accumulate || (!bias && !act && !l2norm), "accumulate excludes bias/act/l2norm");
+    PS_REQUIRE(act >= 0 && act <= 2 && (act != 2 || (!bias && !l2norm)), "act must be 0, 1 or 2 (2 excludes bias/l2norm)");
     PS_REQUIRE(splits == 1 || accumulate, "split-K needs accumulate");
     GemmArgs a{P, ldp, p_rows, Q, ldq, q_rows, C, ldc, M, N, K, bias, norm_out, act, l2norm, accumulate, 0};
     int64_t kps = ps_ceil_div(ps_ceil_div(K, splits), BK) * BK;

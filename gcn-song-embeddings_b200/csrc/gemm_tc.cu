@@ -43,6 +43,7 @@ struct TcArgs {
     int kb_per_split;   // k-blocks (of BK) per split
     int64_t mt, nt, zs;  // work grid: M tiles x N tiles x K splits
     const uint8_t* bpack;  // BPACK kernels: hi/lo images of the Q operand, one [2][BN x 128 B] block per (n-tile, k-block)
+    uint32_t* mask; int64_t ldm;  // optional sign mask of the activation, one bit per output element (ldm in 32-bit words)
 };
 
 // ---------------------------------------------------------------- PTX wrappers
@@ -284,7 +285,7 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 // BPACK: the Q operand (a weight matrix) was split into hi/lo and laid out as K-major SWIZZLE_128B tile images by
 // pack_b_kernel; one thread streams the image of every k-block into the stage with ONE bulk copy, and the eight
 // producer warps only move the activation operand, double-buffered in registers across k-blocks and tiles.
-template <bool PK, bool QK, int BN, bool BPACK>
+template <bool PK, bool QK, int BN, bool BPACK, int MASK>  // MASK: 0 none, 1 = write sign bits (act 1), 2 = apply them (act 2)
 __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(TcArgs a) {
     static_assert(!BPACK || (PK && QK), "packed-B kernels take a K-major P and lay Q out K-major");
     constexpr int STAGES = BN == 256 ? 2 : 3;
@@ -583,6 +584,25 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(TcArgs a) {
                 acc[j] = x;
                 ss = fmaf(x, (col0 + j < a.N) ? x : 0.f, ss);
             }
+            if (MASK) {  // compile-time: only the kernels launched with a sign mask carry this code
+                uint32_t* mrow = a.mask + row * a.ldm + col0 / 32;
+                if (MASK == 1) {  // record sign(activation): the backward applies leaky' from these bits
+#pragma unroll
+                    for (int q = 0; q < HALF / 32; ++q) {
+                        uint32_t bits = 0;
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) bits |= (acc[32 * q + j] > 0.f ? 1u : 0u) << j;
+                        if (row_ok && col0 + 32 * q < a.N) mrow[q] = bits;
+                    }
+                } else {  // act == 2: sum * leaky'(y), y > 0 recorded by the forward
+#pragma unroll
+                    for (int q = 0; q < HALF / 32; ++q) {
+                        const uint32_t bits = (row_ok && col0 + 32 * q < a.N) ? __ldg(mrow + q) : 0u;
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) acc[32 * q + j] *= ((bits >> j) & 1u) ? 1.f : PS_LEAKY_SLOPE;
+                    }
+                }
+            }
             float inv_norm = 1.f;
             if (a.l2norm) {  // the row is split over two threads (column halves): combine through shared memory
                 float* sb = ss_buf + tile_par * 256;
@@ -617,6 +637,10 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(TcArgs a) {
                             float* dst = a.C + grow * a.ldc + gcol;
                             if (a.accumulate) {
                                 atomicAdd(dst + 0, v.x); atomicAdd(dst + 1, v.y); atomicAdd(dst + 2, v.z); atomicAdd(dst + 3, v.w);
+                            } else if (MASK == 0 && a.act == 2) {  // C holds leaky_relu outputs y: C = acc * leaky'(y)
+                                const float4 y = *reinterpret_cast<const float4*>(dst);
+                                *reinterpret_cast<float4*>(dst) = make_float4(v.x * ps_leaky_grad_from_out(y.x), v.y * ps_leaky_grad_from_out(y.y),
+                                                                              v.z * ps_leaky_grad_from_out(y.z), v.w * ps_leaky_grad_from_out(y.w));
                             } else {
                                 *reinterpret_cast<float4*>(dst) = v;
                             }
@@ -688,12 +712,12 @@ static int pack_scratch(cudaStream_t stream, size_t bytes, void** out) {
     return PS_OK;
 }
 
-template <bool PK, bool QK, int BN, bool BPACK>
+template <bool PK, bool QK, int BN, bool BPACK, int MASK = 0>
 int launch_tc(TcArgs a, int q_kmajor, cudaStream_t stream) {
     constexpr int STAGES = BN == 256 ? 2 : 3;
     constexpr size_t smem = STAGES * (2 * BM * 128 + 2 * BN * 128) + (2 * STAGES + 4) * 8 + 16 + (2 * 2 * 128 + 2 * BN + 8 * 32 * kEpiStride) * 4 + 1024;
     static_assert(smem <= 232448, "shared memory budget");
-    auto kern = gemm_tc_kernel<PK, QK, BN, BPACK>;
+    auto kern = gemm_tc_kernel<PK, QK, BN, BPACK, MASK>;
     static bool configured = false;
     static int sms = 148;
     if (!configured) {
@@ -737,8 +761,9 @@ int ps_gemm_tc_launch(const float* P, int64_t ldp, int p_kmajor, const int32_t* 
                       const float* Q, int64_t ldq, int q_kmajor, const int32_t* q_rows,
                       float* C, int64_t ldc, int64_t M, int64_t N, int64_t K,
                       const float* bias, int act, int l2norm, float* norm_out, int accumulate, int splits,
-                      cudaStream_t stream) {
+                      uint32_t* mask, int64_t ldm, cudaStream_t stream) {
     if (M <= 0 || N < 64 || K < 32) return PS_ERR_UNSUPPORTED;                 // tiny problems: not worth a 128-wide tile
+    if (mask != nullptr && (N % 32 != 0 || (act != 1 && act != 2) || l2norm)) return PS_ERR_UNSUPPORTED;
     if ((ldp | ldq | ldc | N) % 4 != 0) return PS_ERR_UNSUPPORTED;
     if ((p_kmajor || q_kmajor) && K % 4 != 0) return PS_ERR_UNSUPPORTED;
     if (!p_kmajor && M % 4 != 0) return PS_ERR_UNSUPPORTED;
@@ -746,6 +771,7 @@ int ps_gemm_tc_launch(const float* P, int64_t ldp, int p_kmajor, const int32_t* 
     if (l2norm && N > 256) return PS_ERR_UNSUPPORTED;
     if (q_kmajor && q_rows) return PS_ERR_UNSUPPORTED;  // row pointers of Q are not precomputed
     if (accumulate && (bias || act || l2norm)) return PS_ERR_UNSUPPORTED;
+    if (act == 2 && (bias || l2norm)) return PS_ERR_UNSUPPORTED;
     if (splits > 1 && !accumulate) return PS_ERR_UNSUPPORTED;
     // The tensor core's TMEM accumulator truncates on every add (measured: ~2e-8 relative per MMA, biased
     // towards zero), so a long accumulation chain drifts: K = 10 000 in one CTA gave 7e-5.  Keep chains at
@@ -755,7 +781,7 @@ int ps_gemm_tc_launch(const float* P, int64_t ldp, int p_kmajor, const int32_t* 
     if (!accumulate && K > 4 * kMaxChainK) return PS_ERR_UNSUPPORTED;
     if (accumulate && ps_ceil_div(K, splits < 1 ? 1 : splits) > kMaxChainK) splits = static_cast<int>(ps_ceil_div(K, kMaxChainK));
     const int BN = (N > 128) ? 256 : 128;
-    TcArgs a{P, ldp, p_rows, Q, ldq, q_rows, C, ldc, M, N, K, bias, norm_out, act, l2norm, accumulate, 0, 0, 0, 0, nullptr};
+    TcArgs a{P, ldp, p_rows, Q, ldq, q_rows, C, ldc, M, N, K, bias, norm_out, act, l2norm, accumulate, 0, 0, 0, 0, nullptr, mask, ldm};
     const int64_t num_kb = ps_ceil_div(K, BK);
     if (splits < 1) splits = 1;
     a.kb_per_split = static_cast<int>(ps_ceil_div(num_kb, splits));
@@ -763,7 +789,14 @@ int ps_gemm_tc_launch(const float* P, int64_t ldp, int p_kmajor, const int32_t* 
     a.mt = ps_ceil_div(M, BM);
     a.nt = ps_ceil_div(N, BN);
     // weight operand (no gather, no split-K) against a tall K-major activation: pre-packed hi/lo images + bulk copies
-    if (g_tc_pack && p_kmajor && q_rows == nullptr && !accumulate && a.zs == 1 && M >= 1024)
+    const bool packable = p_kmajor && q_rows == nullptr && !accumulate && a.zs == 1;
+    if (mask != nullptr) {  // the sign-mask epilogue lives in the packed-weight kernels only
+        if (!packable) return PS_ERR_UNSUPPORTED;
+        if (act == 1)
+            return BN == 256 ? launch_tc<true, true, 256, true, 1>(a, q_kmajor, stream) : launch_tc<true, true, 128, true, 1>(a, q_kmajor, stream);
+        return BN == 256 ? launch_tc<true, true, 256, true, 2>(a, q_kmajor, stream) : launch_tc<true, true, 128, true, 2>(a, q_kmajor, stream);
+    }
+    if (g_tc_pack && packable && M >= 1024)
         return BN == 256 ? launch_tc<true, true, 256, true>(a, q_kmajor, stream) : launch_tc<true, true, 128, true>(a, q_kmajor, stream);
 #define PS_TC_CASE(pk, qk)                                                         \
     if (static_cast<bool>(p_kmajor) == pk && static_cast<bool>(q_kmajor) == qk)     \

@@ -230,6 +230,17 @@ class PinSage():
             self._pos_src = self.positives
         return self._pos_dev
 
+    def prefetch_async(self, batch=None):
+        """prefetch() on a background host thread: returns a Future whose result train_batch() accepts.  The batch
+        preparation holds ~100 small launches and 3 host syncs (the sizes of the three frontiers); with two batches
+        in flight on the worker the training thread never waits for them, it only enqueues the step's kernels."""
+        if getattr(self, "_prep_pool", None) is None:
+            from concurrent.futures import ThreadPoolExecutor
+            dev = torch.cuda.current_device()
+            self._prep_pool = ThreadPoolExecutor(max_workers=1, thread_name_prefix="ps_prepare",
+                                                 initializer=lambda: torch.cuda.set_device(dev))
+        return self._prep_pool.submit(self.prefetch, batch)
+
     def prefetch(self, batch=None):
         """Start preparing the NEXT batch (frontier plans, backward transposes: index work that does not depend
         on the weights) on a side stream while the current step's kernels run.  With batch=None a batch is drawn
@@ -254,6 +265,8 @@ class PinSage():
         """One optimiser step on a batch of (q, pos, neg) triples (pinsage_training.py:181-214).  `batch` is an
         int64 [B,3] tensor (host or device) or a handle from prefetch().  Returns (loss, node_feat_loss,
         variance) as 0-dim device tensors."""
+        if hasattr(batch, "result"):  # a Future from prefetch_async()
+            batch = batch.result()
         prep = batch if hasattr(batch, "plan") else self.prefetch(batch)
         batch = prep.batch
         feats = self._feats()
@@ -275,7 +288,8 @@ class PinSage():
     def train(self):
         """Train the model (pinsage_training.py:216-256)."""
         print("\033[0;33mTraining PinSage...\033[0m")
-        nxt = self.prefetch()
+        from collections import deque
+        pending = deque([self.prefetch_async(), self.prefetch_async()])  # two batches in preparation at any time
         while self.e < self.epochs:
             print(f"Training epoch {self.e+1}/{self.epochs}...")
             cur_lr = self.optimizer.param_groups[0]["lr"]
@@ -283,9 +297,8 @@ class PinSage():
             pbar = tqdm(total=self.b_per_e)
             pbar.update(1)
             while self.b < self.b_per_e:
-                cur = nxt
-                loss, node_feat_loss, variance = self.train_batch(cur)  # launches this step's kernels ...
-                nxt = self.prefetch()                                    # ... and prepares the next batch meanwhile
+                loss, node_feat_loss, variance = self.train_batch(pending.popleft())  # launches this step's kernels ...
+                pending.append(self.prefetch_async())                                 # ... while the worker prepares the next batches
                 pbar.update(1)
                 if self.b % 50 == 0:  # reading the loss synchronises the device: not every step
                     pbar.set_description(f"Loss = {float(loss)}, bathes done")

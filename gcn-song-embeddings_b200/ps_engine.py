@@ -203,7 +203,11 @@ class Engine:
             conv = m.conv_layers[l]
             din = in_dims[l]
             z = torch.empty((lp.nz, dh), dtype=torch.float32, device="cuda")
-            nat.gemm(h_prev, conv.Q.weight, z, lp.nz, dh, din, p_rows=lp.zrows, bias=conv.Q.bias, act=1, tag=f"gemm_q_fwd_l{l}")
+            # training: the GEMM also records sign(z) (1 bit per element) so the backward never re-reads z for leaky'
+            zmask = None
+            if keep and nat.gemm_mask_supported(lp.nz, dh, din) and nat.gemm_mask_supported(lp.nz, dh, do):
+                zmask = torch.empty((lp.nz, dh // 32), dtype=torch.int32, device="cuda")
+            nat.gemm(h_prev, conv.Q.weight, z, lp.nz, dh, din, p_rows=lp.zrows, bias=conv.Q.bias, act=1, mask=zmask, tag=f"gemm_q_fwd_l{l}")
             cat = torch.empty((lp.n, din + dh), dtype=torch.float32, device="cuda")
             inv_wsum = torch.empty((lp.n,), dtype=torch.float32, device="cuda")
             nat.aggregate_fwd(h_prev, lp.self_rows, din, z, lp.nbz, lp.w, dh, cat, inv_wsum, tag=f"aggregate_fwd_l{l}")
@@ -215,7 +219,7 @@ class Engine:
                 nat.gemm(cat, conv.W.weight, h, lp.n, do, din + dh, bias=conv.W.bias, act=1)
                 nat.l2norm_rows(h, norm)
             if keep:
-                saved.append((h_prev, z, cat, inv_wsum, h, norm))
+                saved.append((h_prev, z, cat, inv_wsum, h, norm, zmask))
             h_prev = h
         n_top = plan.layers[-1].n
         a1 = torch.empty((n_top, do), dtype=torch.float32, device="cuda")
@@ -251,23 +255,32 @@ class Engine:
             lp = plan.layers[l]
             conv = m.conv_layers[l]
             din = in_dims[l]
-            h_in, z, cat, inv_wsum, h, norm = saved[l]
+            h_in, z, cat, inv_wsum, h, norm, zmask = saved[l]
             pre = f"conv_layers.{l}."
             d_pre = torch.empty((lp.n, do), dtype=torch.float32, device="cuda")
             nat.norm_leaky_bwd(h, norm, d_h, d_pre)
             nat.gemm(d_pre, cat, grads[pre + "W.weight"], do, din + dh, lp.n, p_kmajor=False, q_kmajor=False,
                      accumulate=True, splits=_splits_for(do, din + dh, lp.n), tag=f"gemm_w_wgrad_l{l}")
             nat.colsum(d_pre, grads[pre + "W.bias"])
-            d_cat = torch.empty((lp.n, din + dh), dtype=torch.float32, device="cuda")
-            nat.gemm(d_pre, conv.W.weight, d_cat, lp.n, din + dh, do, q_kmajor=False, tag=f"gemm_w_dgrad_l{l}")
-            nat.aggregate_bwd(d_cat, din, dh, lp.seg_off, lp.pair_q, lp.w, inv_wsum, lp.w.shape[1], z, chunk_off=lp.chunk_off, chunk_row=lp.chunk_row, tag=f"aggregate_bwd_l{l}")  # z := dZ_pre
+            # Backward of the aggregation.  d_cat[:, din:] = d_pre . W[:, din:] is linear in d_pre, so the weighted
+            # segment sum runs on the do-wide d_pre rows (4x fewer gathered bytes than the dh-wide d_cat rows, and
+            # d_pre fits in L2) and ONE GEMM applies the W block per z-row, with leaky'(z) fused into its store:
+            #   S[u]      = sum_{(t,s) -> u} w[t,s] / wsum[t] * d_pre[t]                    [nz, do]
+            #   dZ_pre[u] = (S[u] . W[:, din:]) * leaky'(z[u])                              [nz, dh]   (in place in z)
+            s_buf = torch.empty((lp.nz, do), dtype=torch.float32, device="cuda")
+            nat.aggregate_bwd(d_pre, 0, do, lp.seg_off, lp.pair_q, lp.w, inv_wsum, lp.w.shape[1], s_buf, chunk_off=lp.chunk_off,
+                              chunk_row=lp.chunk_row, apply_leaky=False, tag=f"aggregate_bwd_l{l}")
+            nat.gemm(s_buf, conv.W.weight.detach()[:, din:], z, lp.nz, dh, do, q_kmajor=False, act=2, mask=zmask,
+                     tag=f"gemm_agg_dgrad_l{l}")  # z := dZ_pre (leaky' from the recorded sign bits, else from z itself)
             nat.gemm(z, h_in, grads[pre + "Q.weight"], dh, din, lp.nz, p_kmajor=False, q_kmajor=False,
                      q_rows=lp.zrows, accumulate=True, splits=_splits_for(dh, din, lp.nz), tag=f"gemm_q_wgrad_l{l}")
             nat.colsum(z, grads[pre + "Q.bias"])
             if l > 0:
                 d_h = torch.empty((lp.nz, din), dtype=torch.float32, device="cuda")
                 nat.gemm(z, conv.Q.weight, d_h, lp.nz, din, dh, q_kmajor=False, tag=f"gemm_q_dgrad_l{l}")
-                nat.scatter_add_rows(d_cat, lp.self_rows, d_h, din)
+                d_self = torch.empty((lp.n, din), dtype=torch.float32, device="cuda")  # d_cat[:, :din]: the self-row gradient
+                nat.gemm(d_pre, conv.W.weight.detach()[:, :din], d_self, lp.n, din, do, q_kmajor=False, tag=f"gemm_w_dgrad_l{l}")
+                nat.scatter_add_rows(d_self, lp.self_rows, d_h, din)
         return grads
 
     def zero_grads(self):

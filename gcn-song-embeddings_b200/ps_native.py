@@ -29,6 +29,9 @@ _SIGNATURES = {
     "ps_last_error": ([], c_char_p),
     "ps_set_device": ([c_int], c_int),
     "ps_gemm_backend": ([c_int], c_int),
+    "ps_gemm_ex": ([c_void_p, c_int64, c_int, c_void_p, c_void_p, c_int64, c_int, c_void_p, c_void_p, c_int64,
+                    c_int64, c_int64, c_int64, c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_void_p, c_int64, c_void_p], c_int),
+    "ps_gemm_mask_supported": ([c_int64, c_int64, c_int64], c_int),
     "ps_gemm_tc_pack": ([c_int], c_int),
     "ps_gemm_tc_waves": ([c_int], c_int),
     "ps_graph_create": ([c_void_p, c_void_p, c_int64, c_int64, c_int64, ctypes.POINTER(c_void_p), c_void_p], c_int),
@@ -41,7 +44,7 @@ _SIGNATURES = {
     "ps_aggregate_fwd": ([c_void_p, c_int64, c_void_p, c_int, c_void_p, c_int64, c_void_p, c_void_p, c_int, c_int,
                           c_int64, c_void_p, c_int64, c_void_p, c_void_p], c_int),
     "ps_aggregate_bwd": ([c_void_p, c_int64, c_int, c_int, c_void_p, c_void_p, c_int, c_int64, c_void_p, c_void_p,
-                          c_void_p, c_int, c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_void_p], c_int),
+                          c_void_p, c_int, c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_int, c_void_p], c_int),
     "ps_norm_leaky_bwd": ([c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_int64, c_int, c_void_p], c_int),
     "ps_l2norm_rows": ([c_void_p, c_int64, c_int64, c_int, c_void_p, c_void_p], c_int),
     "ps_leaky_bwd": ([c_void_p, c_void_p, c_int64, c_void_p], c_int),
@@ -229,17 +232,23 @@ def trace_topt(trace: torch.Tensor, sources: torch.Tensor, T: int):
 # ------------------------------------------------------------------------------------
 
 def gemm(P, Q, C, M, N, K, *, p_kmajor=True, q_kmajor=True, p_rows=None, q_rows=None, bias=None,
-         act=0, l2norm=False, norm_out=None, accumulate=False, splits=1, tag="gemm"):
-    """C[i,j] (+)= act(sum_r P(i,r) Q(j,r) + bias[j]); see ps_gemm in the header."""
+         act=0, l2norm=False, norm_out=None, accumulate=False, splits=1, mask=None, tag="gemm"):
+    """C[i,j] (+)= act(sum_r P(i,r) Q(j,r) + bias[j]); see ps_gemm / ps_gemm_ex in the header.  mask: int32
+    [M, N/32] sign mask of the activation (written with act=1, read with act=2)."""
     with _Timed(tag, 2.0 * M * N * K, 4.0 * (M * K + N * K + M * N)):
-        _gemm(P, Q, C, M, N, K, p_kmajor, q_kmajor, p_rows, q_rows, bias, act, l2norm, norm_out, accumulate, splits)
+        _gemm(P, Q, C, M, N, K, p_kmajor, q_kmajor, p_rows, q_rows, bias, act, l2norm, norm_out, accumulate, splits, mask)
 
 
-def _gemm(P, Q, C, M, N, K, p_kmajor, q_kmajor, p_rows, q_rows, bias, act, l2norm, norm_out, accumulate, splits):
-    check(lib().ps_gemm(_p(P, torch.float32), _ld(P), int(p_kmajor), _p(p_rows, torch.int32),
-                        _p(Q, torch.float32), _ld(Q), int(q_kmajor), _p(q_rows, torch.int32),
-                        _p(C, torch.float32), _ld(C), int(M), int(N), int(K), _p(bias, torch.float32),
-                        int(act), int(l2norm), _p(norm_out, torch.float32), int(accumulate), int(splits), _stream()))
+def gemm_mask_supported(M, N, K) -> bool:
+    return bool(lib().ps_gemm_mask_supported(int(M), int(N), int(K)))
+
+
+def _gemm(P, Q, C, M, N, K, p_kmajor, q_kmajor, p_rows, q_rows, bias, act, l2norm, norm_out, accumulate, splits, mask=None):
+    check(lib().ps_gemm_ex(_p(P, torch.float32), _ld(P), int(p_kmajor), _p(p_rows, torch.int32),
+                           _p(Q, torch.float32), _ld(Q), int(q_kmajor), _p(q_rows, torch.int32),
+                           _p(C, torch.float32), _ld(C), int(M), int(N), int(K), _p(bias, torch.float32),
+                           int(act), int(l2norm), _p(norm_out, torch.float32), int(accumulate), int(splits),
+                           _p(mask, torch.int32), _ld(mask) if mask is not None else 0, _stream()))
 
 
 def gemm_backend(mode: int) -> int:
@@ -285,19 +294,19 @@ def aggregate_bwd_chunk_rows(chunk_off, pairs, nz, chunk_pairs=AGG_BWD_CHUNK):
 
 
 def aggregate_bwd(dcat, col_off, dh, seg_off, pair_q, nbw, inv_wsum, T, z, chunk_off=None, chunk_pairs=AGG_BWD_CHUNK,
-                  chunk_row=None, tag="aggregate_bwd"):
+                  chunk_row=None, apply_leaky=True, tag="aggregate_bwd"):
     pairs, nz = pair_q.numel(), z.shape[0]
     if chunk_off is None:
         chunk_off = aggregate_bwd_chunks(seg_off, chunk_pairs)
     max_chunks = pairs // chunk_pairs + nz  # upper bound of chunk_off[-1], known without a device read
     ws = torch.empty((max(max_chunks, 1), dh), dtype=torch.float32, device=z.device)
     # algorithmic bytes: one dh-wide dcat row per (target, slot) pair + pair index/weight/inv_wsum, Z read + written
-    with _Timed(tag, 2.0 * pairs * dh, float(pairs) * (dh * 4 + 12) + float(nz) * (2 * dh * 4 + 8)):
+    with _Timed(tag, 2.0 * pairs * dh, float(pairs) * (dh * 4 + 12) + float(nz) * ((2 if apply_leaky else 1) * dh * 4 + 8)):
         check(lib().ps_aggregate_bwd(_p(dcat, torch.float32), _ld(dcat), int(col_off), int(dh),
                                      _p(seg_off, torch.int32), _p(chunk_off, torch.int32), int(chunk_pairs), int(max_chunks),
                                      _p(pair_q, torch.int32), _p(nbw, torch.float32), _p(inv_wsum, torch.float32), int(T),
                                      _p(z, torch.float32), _ld(z), int(nz), _p(ws, torch.float32),
-                                     _p(chunk_row, torch.int32), _stream()))
+                                     _p(chunk_row, torch.int32), int(apply_leaky), _stream()))
 
 
 def norm_leaky_bwd(h, norm, dh, dpre):

@@ -69,7 +69,9 @@ int ps_trace_topt(const int64_t* trace, const int64_t* sources, int64_t n, int n
  *        C[i, j] (+)= act( sum_{r<K} P(i, r) * Q(j, r) + bias[j] )
  *      P(i, r) = p_kmajor ? P[prow(i)*ldp + r] : P[prow(r)*ldp + i]   (same for Q),
  *      prow(x) = p_rows ? p_rows[x] : x  (row gather folded into the operand load, K4).
- *      act: 0 none, 1 leaky_relu(0.01).  l2norm: divide each output row by its L2 norm
+ *      act: 0 none, 1 leaky_relu(0.01), 2 = C holds leaky_relu outputs y on entry and receives
+ *      sum * leaky'(y) (backward through the activation fused into the store; no bias / l2norm).
+ *      l2norm: divide each output row by its L2 norm
  *      (requires N <= 128; norm_out[i] receives the norm, may be NULL).
  *      accumulate: atomically add into C instead of storing (bias/act/l2norm must be off);
  *      splits > 1 partitions K over CTAs (needs accumulate).
@@ -80,6 +82,18 @@ int ps_gemm(const float* P, int64_t ldp, int p_kmajor, const int32_t* p_rows,
             float* C, int64_t ldc, int64_t M, int64_t N, int64_t K,
             const float* bias, int act, int l2norm, float* norm_out, int accumulate, int splits,
             ps_stream_t stream);
+
+/* ps_gemm with a sign mask of the activation (one bit per output element, row-major, ld_mask 32-bit words per row,
+ * bit (j % 32) of word j / 32 = column j):  act = 1 additionally WRITES mask = (output > 0);  act = 2 READS it and
+ * stores sum * leaky'(mask) without touching the old contents of C.  The forward Q GEMM records the mask and the
+ * aggregation backward consumes it, which saves re-reading the dh-wide activations.  Tensor-core path only:
+ * ps_gemm_mask_supported(M, N, K) tells whether a shape qualifies (N % 32 == 0 among others); mask = NULL is ps_gemm. */
+int ps_gemm_mask_supported(int64_t M, int64_t N, int64_t K);
+int ps_gemm_ex(const float* P, int64_t ldp, int p_kmajor, const int32_t* p_rows,
+               const float* Q, int64_t ldq, int q_kmajor, const int32_t* q_rows,
+               float* C, int64_t ldc, int64_t M, int64_t N, int64_t K,
+               const float* bias, int act, int l2norm, float* norm_out, int accumulate, int splits,
+               uint32_t* mask, int64_t ld_mask, ps_stream_t stream);
 
 /* Select the ps_gemm implementation: 0 (default) = tcgen05 tensor cores with the 3xTF32
  * error-compensated split wherever the shape allows (CUDA cores otherwise), 1 = CUDA-core
@@ -111,12 +125,15 @@ int ps_aggregate_fwd(const float* hin, int64_t ld_hin, const int32_t* self_rows,
  *      max_chunks >= chunk_off[n_zrows] sizes the launch (no host sync needed) and
  *      partial_ws holds max_chunks * dh floats of scratch for rows that span several chunks.
  *      chunk_row (optional, int32 [max_chunks]): the z-row that owns every chunk
- *      (last u with chunk_off[u] <= chunk); NULL = searched per chunk. ---- */
+ *      (last u with chunk_off[u] <= chunk); NULL = searched per chunk.
+ *      apply_leaky = 0 turns the kernel into the plain segmented sum  z[u, :] = sum_q ...  (z is output only):
+ *      the engine uses it on the do-wide d(pre-activation) rows and applies the W block + leaky' afterwards
+ *      with ps_gemm(act = 2), which moves 4x fewer bytes than gathering the dh-wide dcat rows. ---- */
 int ps_aggregate_bwd(const float* dcat, int64_t ldcat, int col_off, int dh,
                      const int32_t* seg_off, const int32_t* chunk_off, int chunk_pairs, int64_t max_chunks,
                      const int32_t* pair_q, const float* nbw, const float* inv_wsum, int T,
                      float* z, int64_t ldz, int64_t n_zrows, float* partial_ws, const int32_t* chunk_row,
-                     ps_stream_t stream);
+                     int apply_leaky, ps_stream_t stream);
 /* backward of  h = y / ||y||,  y = leaky_relu(pre)  (pinsage_model.py:209-210):
  *   dpre = leaky'(h) * (dh - h * (h . dh)) / norm */
 int ps_norm_leaky_bwd(const float* h, int64_t ldh, const float* norm, const float* dh, int64_t lddh,

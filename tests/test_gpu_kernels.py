@@ -48,6 +48,39 @@ def test_gemm_layouts(nat, backend, M, N, K, pk, qk):
     assert rel(C, want) < 1e-5
 
 
+@pytest.mark.parametrize("M,N,K", [(3000, 512, 128), (70, 64, 32), (4096, 96, 128)])
+def test_gemm_act2_masks_by_existing_output(nat, backend, M, N, K):
+    """act = 2: C holds leaky_relu outputs y and receives (P Q^T) * leaky'(y); Q given as a column block of a wider
+    MN-major matrix (how the engine applies W[:, din:] in the aggregation backward)."""
+    torch.manual_seed(M + N)
+    S = torch.randn(M, K, device="cuda")
+    W = torch.randn(K, 256 + N, device="cuda")            # [do, din + dh]
+    y = leaky(torch.randn(M, N, device="cuda"))
+    C = y.clone()
+    nat.gemm(S, W[:, 256:], C, M, N, K, q_kmajor=False, act=2)
+    want = (S.double() @ W[:, 256:].double()) * torch.where(y > 0, 1.0, 0.01).double()
+    assert rel(C, want) < 1e-5
+
+
+def test_gemm_sign_mask_roundtrip(nat):
+    """ps_gemm_ex: act=1 records sign(output) as one bit per element; act=2 with that mask stores sum * leaky'
+    without reading C (what the engine's forward / aggregation-backward pair does)."""
+    torch.manual_seed(5)
+    for M, N, K in ((2000, 512, 256), (130, 64, 32), (1500, 96, 64)):
+        assert nat.gemm_mask_supported(M, N, K)
+        X = torch.randn(M, K, device="cuda"); W = torch.randn(N, K, device="cuda"); b = torch.randn(N, device="cuda")
+        y = torch.empty(M, N, device="cuda"); mask = torch.zeros(M, N // 32, dtype=torch.int32, device="cuda")
+        nat.gemm(X, W, y, M, N, K, bias=b, act=1, mask=mask)
+        bits = ((mask.view(M, N // 32, 1) >> torch.arange(32, device="cuda", dtype=torch.int32)) & 1).reshape(M, N).bool()
+        assert torch.equal(bits, y > 0)
+        S = torch.randn(M, 64, device="cuda"); V = torch.randn(64, N, device="cuda")
+        out = torch.full((M, N), float("nan"), device="cuda")   # never read
+        nat.gemm(S, V, out, M, N, 64, q_kmajor=False, act=2, mask=mask)
+        want = (S.double() @ V.double()) * torch.where(y > 0, 1.0, 0.01).double()
+        assert rel(out, want) < 1e-5
+    assert not nat.gemm_mask_supported(100, 48, 64)
+
+
 def test_gemm_gather_bias_act_norm(nat, backend):
     torch.manual_seed(1)
     table = torch.randn(5000, 256, device="cuda")
@@ -169,6 +202,12 @@ def test_aggregate_bwd_skewed_segments(nat):
     again = z.clone()
     nat.aggregate_bwd(dcat, din, dh, seg, order.to(torch.int32), w, inv, T, again, chunk_pairs=64)
     assert torch.equal(again, outs[0])  # deterministic (no atomics)
+    # apply_leaky = False: the plain segmented sum into an output-only buffer (what the engine runs on d_pre)
+    plain = torch.full((nz, dh), 7.0, device="cuda")
+    nat.aggregate_bwd(dcat, din, dh, seg, order.to(torch.int32), w, inv, T, plain, chunk_pairs=64, apply_leaky=False)
+    want_plain = torch.zeros(nz, dh, device="cuda", dtype=torch.float64).index_add_(
+        0, flat.long(), coef[:, None] * dcat[:, din:].double().repeat_interleave(T, 0))
+    assert rel(plain, want_plain) < 1e-5 and bool((plain[nz // 2:] == 0).all())
     # precomputed chunk -> row map (what the engine passes) == the in-kernel search, bit for bit
     mapped = z.clone()
     coff = nat.aggregate_bwd_chunks(seg, 64)
