@@ -56,6 +56,7 @@ _SIGNATURES = {
     "ps_sample_batch_workspace": ([c_int], c_int64),
     "ps_sample_batch": ([c_void_p, c_int64, c_void_p, c_int64, c_int, c_uint64, c_uint64, c_void_p, c_void_p, c_int64,
                          c_void_p, c_void_p], c_int),
+    "ps_topk_rows": ([c_void_p, c_int64, c_int64, c_int64, c_int, c_void_p, c_void_p, c_void_p], c_int),
     "ps_adam_step": ([c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_float, c_float, c_float, c_float, c_int64,
                       c_float, c_void_p], c_int),
 }
@@ -361,6 +362,16 @@ def sample_batch(positives, all_ids, n_items, B, seed, step, out=None):
 
 def sample_batch_supported(P, n_items, B):
     return 0 < B <= 2600 and 16 * B <= P < 0xFFFFFFFF and 16 * B <= n_items < (1 << 31)
+
+
+def topk_rows(x, k):
+    """ps_topk_rows: (values float32 [n, k], indices int64 [n, k]) of the k largest entries of every row of x."""
+    _ensure_device()
+    n, m = x.shape
+    val = torch.empty((n, k), dtype=torch.float32, device="cuda")
+    idx = torch.empty((n, k), dtype=torch.int64, device="cuda")
+    check(lib().ps_topk_rows(_p(x, torch.float32), _ld(x), int(n), int(m), int(k), _p(val), _p(idx), _stream()))
+    return val, idx
 
 
 def adam_step(param, grad, exp_avg, exp_avg_sq, lr, beta1, beta2, eps, step, grad_scale=1.0):

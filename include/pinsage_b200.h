@@ -175,6 +175,13 @@ int ps_sample_batch(const int64_t* positives, int64_t P, const int64_t* all_ids,
                     uint64_t seed, uint64_t step, int64_t* out_batch, void* workspace, int64_t workspace_bytes,
                     int* short_flag, ps_stream_t stream);
 
+/* ---- K14: per-row top-k of a row-major float matrix (the selection half of the cosine kNN search,
+ *      baselines.py:91-103: cosine_sim.topk(k+1, dim=1); the similarity tile is a ps_gemm).
+ *      out_val / out_idx [n_rows, k]: the k largest values of every row in descending order, ties by ascending
+ *      column; NaN sorts as the largest value (as torch.topk).  1 <= k <= min(8192, n_cols), n_cols < 2^32. ---- */
+int ps_topk_rows(const float* x, int64_t ld, int64_t n_rows, int64_t n_cols, int k,
+                 float* out_val, int64_t* out_idx, ps_stream_t stream);
+
 /* ---- K13: Adam step on a flat fp32 parameter buffer (torch.optim.Adam defaults:
  *      betas, eps, no weight decay, no amsgrad; pinsage_training.py:147,191).
  *      step is the 1-based step count used for bias correction. ---- */

@@ -141,3 +141,26 @@ def test_ppr_baseline_and_generate_positives(tmp_path):
     assert all(idx[p["b"]] in nb_all[idx[p["a"]], :3].tolist() for p in pairs)
     gp.generate_random_positives(d, n=50)
     assert len(json.load(open(os.path.join(d, "positives_random.json")))) == 50
+
+
+@pytest.mark.parametrize("n_rows,n_cols,k", [(7, 1000, 10), (64, 50_000, 1001), (3, 33, 33), (5, 4099, 128)])
+def test_topk_rows_matches_torch(n_rows, n_cols, k):
+    """ps_topk_rows == torch.topk (values bit-equal; indices equal, ties by ascending column)."""
+    import ps_native as nat
+    torch.manual_seed(n_cols)
+    x = torch.randn(n_rows, n_cols, device="cuda")
+    x[0, :5] = 3.0                      # exact ties above the threshold region
+    if n_cols > 200:
+        x[1, 100:160] = x[1].kthvalue(n_cols - k + 1).values  # many elements equal to the k-th value
+    val, idx = nat.topk_rows(x, k)
+    tv, ti = x.topk(k, dim=1)
+    assert torch.equal(val, tv)
+    assert torch.equal(x.gather(1, idx), val)                      # indices point at the values
+    assert all(len(set(r)) == k for r in idx.tolist())             # no column twice
+    # ties resolved by ascending column: (value desc, column asc) is a strict order
+    same = val[:, 1:] == val[:, :-1]
+    assert bool((idx[:, 1:][same] > idx[:, :-1][same]).all())
+    # a padded (strided) view, as a sub-tile of a larger buffer
+    big = torch.randn(n_rows, n_cols + 12, device="cuda")
+    v2, i2 = nat.topk_rows(big[:, :n_cols], k)
+    assert torch.equal(v2, big[:, :n_cols].topk(k, dim=1).values)
