@@ -23,6 +23,11 @@ from __future__ import annotations
 import argparse
 import json
 import os
+
+# More hardware work queues than the default 8 before the CUDA context exists: the batch-preparation stream must not
+# share a queue with the training stream (measured: when the two alias, every host sync of the preparation waits for
+# a whole queued train step and the step time doubles).  ps_native does the same for library users.
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
 import statistics
 import subprocess
 import sys
@@ -290,9 +295,12 @@ def run_ours(args, wl):
         host["train"] += h1 - h0; host["prefetch"] += time.perf_counter() - h1
         return out
 
+    for _ in range(args.setup_steps):  # untimed: lets the caching allocator reach its steady state on both streams
+        device_step()                  # (a cudaMalloc inside a step synchronises the device and stalls the pipeline)
     for _ in range(args.warmup):
         device_step()
     torch.cuda.synchronize(); ps_dist.barrier()
+    dev_allocs0 = torch.cuda.memory_stats().get("num_device_alloc", 0)
 
     # ---- timed region: K steps, device-resident inputs ----
     sampler = ClockSampler(local) if rank == 0 else None
@@ -312,6 +320,7 @@ def run_ours(args, wl):
     wall = time.perf_counter() - w0
     dev_ms = t0.elapsed_time(t1)
     launches = ps_native.launch_count - launches0
+    dev_allocs = torch.cuda.memory_stats().get("num_device_alloc", 0) - dev_allocs0
     host_ms = {k: round(v * 1e3 / args.steps, 3) for k, v in host.items()}
     clocks = sampler.stop() if sampler else None
     prof = ps_native.profiler.summary(); ps_native.profiler = None
@@ -373,7 +382,11 @@ def run_ours(args, wl):
                      "sources": N, "n_hops": 500, "alpha": 0.85, "T": 100, "ms": round(walk_ms, 3),
                      "algorithmic_gbs": round(walk_steps_per_s * 28 / 1e9, 2),
                      "frac_of_hbm": round(walk_steps_per_s * 28 / 1e9 / peaks["hbm_gbs"], 4)},
-            "final_loss": final_loss, "host_ms_per_step": host_ms}
+            "final_loss": final_loss, "host_ms_per_step": host_ms, "cudaMallocs_in_timed_region": dev_allocs}
+    import ps_engine
+    if ps_engine._PREP_TIMING is not None and ps_engine._PREP_TIMING["n"]:
+        t = ps_engine._PREP_TIMING
+        line["prep_timing_ms"] = {k: round(v * 1e3 / t["n"], 3) for k, v in t.items() if k != "n"}
     if rank == 0:
         line["roofline"] = roofline_from_profile(prof, args.steps, peaks)
         if world == 1 and not args.no_cpu_baseline:
@@ -452,6 +465,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cfg3", choices=sorted(WORKLOADS))
     ap.add_argument("--mode", default="train", choices=["train", "infer"], help="infer = node-range sharded full-graph embedding (cfg4 / cfg4q)")
+    ap.add_argument("--setup-steps", type=int, default=8, help="extra untimed steps before the W warm-up steps (allocator steady state)")
     ap.add_argument("--exchange", action="store_true", help="infer mode: all-gather layer outputs instead of recomputing the closure")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--tc-waves", type=int, default=0, help="override ps_gemm_tc_waves (development)")

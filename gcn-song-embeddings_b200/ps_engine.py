@@ -21,12 +21,18 @@ Design differences (results identical, see tests/):
 """
 from __future__ import annotations
 
+import os
+import time
 from dataclasses import dataclass, field
 from typing import List, Optional
 
 import torch
 
 import ps_native as nat
+
+
+# PS_PREP_TIMING=1: host-side timing of Engine.prepare (development aid; adds stream syncs)
+_PREP_TIMING = {"sample": 0.0, "unique": 0.0, "plan_host": 0.0, "plan_drain": 0.0, "n": 0} if os.environ.get("PS_PREP_TIMING") else None
 
 
 def _dev(t, dtype=None, device="cuda"):
@@ -324,18 +330,27 @@ class Engine:
             if batch.numel() and (int(batch.max()) >= NeighborTable.of(m.nbhds).n or int(batch.min()) < 0):
                 raise IndexError("node id out of range")
             check_ids = False  # checked on the host copy, no device read needed
+        timing = _PREP_TIMING
+        t0 = time.perf_counter() if timing is not None else 0.0
         with torch.cuda.stream(side):
             if batch is None:
                 batch = sampler()
             batch = batch.to("cuda", torch.int64, non_blocking=True)
             B = batch.shape[0]
+            if timing is not None:
+                side.synchronize(); t1 = time.perf_counter(); timing["sample"] += t1 - t0
             top, inv = torch.unique(batch.reshape(-1), return_inverse=True)
+            if timing is not None:
+                t2 = time.perf_counter(); timing["unique"] += t2 - t1
             triples = inv.view(B, 3).to(torch.int32).contiguous()
             plan = build_plan(top, m.n_layers, m.T, NeighborTable.of(m.nbhds), need_backward=True, check_ids=check_ids)
             counts = torch.empty((3, top.numel()), dtype=torch.int32, device="cuda")
             nat.count_triples(triples, top.numel(), counts)
             ready = torch.cuda.Event()
             ready.record(side)
+            if timing is not None:
+                t3 = time.perf_counter(); timing["plan_host"] += t3 - t2
+                side.synchronize(); timing["plan_drain"] += time.perf_counter() - t3; timing["n"] += 1
         return Prepared(batch=batch, triples=triples, plan=plan, counts=counts, ready=ready)
 
     def train_step(self, feats: torch.Tensor, batch, margin: float, reference_compat: bool = True):

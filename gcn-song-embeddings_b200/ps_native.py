@@ -11,7 +11,11 @@ import os
 import threading
 from ctypes import c_char_p, c_double, c_float, c_int, c_int64, c_uint64, c_void_p
 
-import torch
+# The engine overlaps batch preparation (side stream) with the train step (main stream); with the default 8 hardware
+# work queues the two streams can alias to one queue, which serialises them.  Only effective before CUDA initialises.
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+
+import torch  # noqa: E402
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libpinsage_b200.so")

@@ -1,3 +1,4 @@
-timeout 600 python -m pytest tests/test_gpu_eval.py -m gpu -q -x > gpurun_out/test14.log 2>&1; echo "pytest rc=$?" >> gpurun_out/test14.log
-tail -3 gpurun_out/test14.log; grep -E "^E  " gpurun_out/test14.log | head -5
-timeout 300 python tools/knn_microbench.py > gpurun_out/knn_mb.log 2>&1; cat gpurun_out/knn_mb.log
+for ss in 1 2 3 4; do
+timeout 600 python bench.py --steps 20 --warmup 3 --no-cpu-baseline > gpurun_out/bench19.log 2>&1; tail -1 gpurun_out/bench19.log | python -c "
+import json,sys; d=json.loads(sys.stdin.read()); print('run $ss', d['ms_per_step'], d['e2e']['ms_per_step'], d['host_ms_per_step'], d['cudaMallocs_in_timed_region'])"
+done
