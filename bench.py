@@ -128,9 +128,15 @@ def roofline_from_profile(summary, steps, peaks):
     tag, top = max(summary.items(), key=lambda kv: kv[1]["ms"])
     per_launch_ms = top["ms"] / top["launches"]
     is_gemm = tag.startswith("gemm")
+    extra = {}
     if is_gemm:
         achieved = top["flops"] / top["launches"] / (per_launch_ms * 1e-3) / 1e12
         peak, unit, bound = peaks["tflops"], "TFLOP/s", "tensor"
+        # fp32 parity needs the 3xTF32 split: every algorithmic FLOP is 3 tf32 tensor-core FLOPs, and dense tf32 runs at
+        # half the bf16 rate, so the fp32-equivalent ceiling of the tensor pipe is peak / 6
+        extra = {"note": "fp32-in/fp32-out GEMM computed as an error-compensated 3xTF32 product on tcgen05",
+                 "issued_tf32_tflops": round(3 * achieved, 2), "fp32_equivalent_ceiling": round(peak / 6, 1),
+                 "frac_of_fp32_equivalent_ceiling": round(achieved / (peak / 6), 4)}
     else:
         achieved = top["bytes"] / top["launches"] / (per_launch_ms * 1e-3) / 1e9
         peak, unit, bound = peaks["hbm_gbs"], "GB/s", "hbm"
@@ -138,7 +144,7 @@ def roofline_from_profile(summary, steps, peaks):
     return {"kernel": tag, "bound": bound, "achieved": round(achieved, 2), "peak": peak, "unit": unit,
             "frac": round(achieved / peak, 4), "traffic": measured_traffic(tag), "peak_source": peaks["source"],
             "algorithmic_per_launch": (top["flops"] if is_gemm else top["bytes"]) / top["launches"],
-            "ms_per_launch": round(per_launch_ms, 4), "launches_per_step": top["launches"] / steps,
+            **extra, "ms_per_launch": round(per_launch_ms, 4), "launches_per_step": top["launches"] / steps,
             "share_of_kernel_time": round(top["ms"] / total, 4), "kernel_time_shares": shares,
             "all": {k: {"ms_per_step": round(v["ms"] / steps, 4),
                         "tflops": round(v["flops"] / (v["ms"] * 1e-3) / 1e12, 2) if v["ms"] > 0 else None,
