@@ -224,10 +224,13 @@ def run_reference(args, wl):
     return 0
 
 
+SAMPLING_DESC = ["precomputed neighbourhoods (n_hops=500, alpha=0.85, T_precomp=100), easy negatives"]
+
+
 def workload_config(name, wl, n_gpus):
     return {"workload": f"{name}: synthetic bipartite {wl['n_tracks']} tracks / {wl['n_cols']} playlists / {wl['n_edges']} edges, "
                         f"{wl['din']}-d features, {wl['n_layers']} layers, T={wl['T']}, hidden 512, out 128, batch {wl['batch']}/GPU",
-            "sampling": "precomputed neighbourhoods (n_hops=500, alpha=0.85, T_precomp=100), easy negatives",
+            "sampling": SAMPLING_DESC[0],
             "global_batch": wl["batch"] * n_gpus, "parallelism": f"dp{n_gpus}",
             "l2_policy": "inputs larger than L2 (features 1.0 GB, transformed rows up to 2 GB per step vs 126 MB L2)"}
 
@@ -284,6 +287,7 @@ def run_ours(args, wl):
         os.chdir(cwd)
     trainer.T = T; trainer.model.T = T
     trainer.batch_size = B
+    trainer.online_sampling = args.sampling == "online"
     ps_dist.attach(trainer, rank, world)
     nbhds_cpu = trainer.nbhds
 
@@ -471,6 +475,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cfg3", choices=sorted(WORKLOADS))
     ap.add_argument("--mode", default="train", choices=["train", "infer"], help="infer = node-range sharded full-graph embedding (cfg4 / cfg4q)")
+    ap.add_argument("--sampling", default="precomp", choices=["precomp", "online"],
+                    help="precomp = table lookup of neighbourhoods precomputed once (the reference's default); online = the walker runs inside every step")
     ap.add_argument("--setup-steps", type=int, default=8, help="extra untimed steps before the W warm-up steps (allocator steady state)")
     ap.add_argument("--exchange", action="store_true", help="infer mode: all-gather layer outputs instead of recomputing the closure")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -478,6 +484,8 @@ def main():
     ap.add_argument("--torch-profile", default=None, help="write a torch.profiler kernel table of 3 extra steps here")
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]
+    if args.sampling == "online":
+        SAMPLING_DESC[0] = "online: the walker (n_hops=500, alpha=0.85, top-T) runs inside every step on the frontier of each layer, easy negatives"
     if args.mode == "infer":
         return run_inference(args, wl)
     if args.impl == "reference":

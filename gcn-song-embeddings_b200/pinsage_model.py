@@ -223,12 +223,20 @@ class PinSageModel(nn.Module):
         torch.nn.init.xavier_uniform_(self.G2.weight)
         self.reference_compat = True
         ps_native._ensure_device()  # fail loudly here, not at the first forward
+        if nbhds is None:  # online sampling: the walker runs inside every forward (pinsage_model.py:249-250, commented out there)
+            self.nbhds = self.online_neighbors()
         self.to("cuda")
         self._engine = Engine(self)
 
     @property
     def engine(self) -> Engine:
         return self._engine
+
+    def online_neighbors(self, seed=None):
+        """A neighbourhood provider that samples with the walker on demand (assign it to `self.nbhds`)."""
+        from ps_engine import OnlineNeighbors
+        pg = as_psgraph(self.g, self.n_items)
+        return OnlineNeighbors(pg.device(), self.n_items, self.n_hops, self.alpha, _next_seed() if seed is None else seed)
 
     def forward(self, initial_h, nodeset):
         feats = self._engine.features(initial_h)

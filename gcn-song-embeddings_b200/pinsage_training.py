@@ -196,6 +196,7 @@ class PinSage():
         self.b_per_e = 500
 
         self.embeddings = None
+        self.online_sampling = False   # True: run the walker inside every step (reference's online relevant_nodes_per_layer)
         self.reference_compat = True   # duplicate-node gradient factor, hard-negative row quirk
         self.diagnostics = True        # node-feature loss + batch variance, as train_batch returns them
         self.world_size, self.rank = 1, 0  # set by ps_dist.attach() for data-parallel runs
@@ -259,6 +260,10 @@ class PinSage():
             batch = torch.as_tensor(batch)
         if not self.reference_compat:
             self.model.T = self.T  # the reference never re-reads T after construction (grid_search.py:46-47)
+        if getattr(self, "online_sampling", False) != getattr(self, "_online_active", False):
+            # online: neighbourhoods are re-sampled by the walker inside every step instead of read from the table
+            self.model.nbhds = self.model.online_neighbors() if self.online_sampling else self.nbhds
+            self._online_active = bool(self.online_sampling)
         return self.model.engine.prepare(batch, sampler)
 
     def train_batch(self, batch):

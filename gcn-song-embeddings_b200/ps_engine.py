@@ -54,9 +54,13 @@ class NeighborTable:
         self.n, self.Tp = self.nodes.shape
         self.scratch = {}
 
+    def lookup(self, cur: torch.Tensor, T: int):
+        """(neighbours int32 [n, T], weights float32 [n, T]) of the nodes `cur` (int64 on the device)."""
+        return self.nodes[cur, :T], self.w[cur, :T].contiguous()
+
     @classmethod
     def of(cls, nbhds) -> "NeighborTable":
-        if isinstance(nbhds, NeighborTable):
+        if isinstance(nbhds, (NeighborTable, OnlineNeighbors)):
             return nbhds
         weights, nodes = nbhds
         key = "_ps_table"
@@ -68,6 +72,37 @@ class NeighborTable:
             except Exception:
                 pass
         return cached
+
+
+class OnlineNeighbors:
+    """Neighbourhoods sampled on demand: the walker (ps_walk_topt) runs inside every forward on the nodes of each
+    layer's frontier, like the reference's online `relevant_nodes_per_layer` (pinsage_model.py:142-154, the
+    "sample" of "sample + fwd + bwd").  Same interface as NeighborTable.  One difference from the reference: the
+    q / pos / neg forwards of a training batch share one frontier here, so a node gets ONE fresh neighbourhood per
+    step instead of one per column / layer it appears in (the Philox key changes once per plan; within a plan the
+    walks of a node do not depend on which layer asks, because draws are keyed by (seed, source, step))."""
+
+    def __init__(self, graph_handle, n_items: int, n_hops: int, alpha: float, seed: int = 0x0417E5EED):
+        self.graph, self.n, self.n_hops, self.alpha = graph_handle, int(n_items), int(n_hops), float(alpha)
+        self.Tp = 1 << 30
+        self.scratch = {}
+        self._seed = int(seed)
+
+    def new_plan(self):
+        """Fresh walks for the next plan (called by build_plan)."""
+        self._seed = (self._seed * 6364136223846793005 + 1442695040888963407) & 0xFFFFFFFFFFFFFFFF
+
+    def lookup(self, cur: torch.Tensor, T: int):
+        with nat._Timed("walk_topt_online", 0.0, 28.0 * cur.numel() * self.n_hops):
+            out = nat.walk_topt(self.graph, cur, self.n_hops, self.alpha, T, self._seed, want_i64=False, want_i32=True)
+        return out["nodes_i32"], out["weights_f32"]
+
+    def materialize(self, T: int) -> NeighborTable:
+        """One walker pass over all items -> a fixed table (full-graph inference needs consistent neighbourhoods)."""
+        nodes, w = self.lookup(torch.arange(self.n, device="cuda"), T)
+        table = NeighborTable.__new__(NeighborTable)
+        table.nodes, table.w, table.n, table.Tp, table.scratch = nodes, w, self.n, T, {}
+        return table
 
 
 @dataclass
@@ -121,11 +156,12 @@ def build_plan(top: torch.Tensor, n_layers: int, T: int, table: NeighborTable, n
         if hi >= table.n or lo < 0:
             raise IndexError("node id out of range")  # the reference raises IndexError on OOB ids too
     plan = Plan(top=top, layers=[None] * n_layers)
+    if hasattr(table, "new_plan"):
+        table.new_plan()
     cur = top
     for l in reversed(range(n_layers)):
         n = cur.numel()
-        nb = table.nodes[cur, :T]
-        w = table.w[cur, :T].contiguous()
+        nb, w = table.lookup(cur, T)
         if l > 0:
             allv = torch.cat([nb.reshape(-1).to(torch.int64), cur])
             nxt, inv = _unique_inverse(allv, table.n, table.scratch)
@@ -396,6 +432,8 @@ class Engine:
         rows it would have recomputed arrive from their owners."""
         m = self.model
         table = NeighborTable.of(m.nbhds)
+        if isinstance(table, OnlineNeighbors):
+            table = table.materialize(m.T)
         N, T, L = table.n, m.T, m.n_layers
         in_dims, dh, do = self._dims()
         dev = feats.device

@@ -188,3 +188,34 @@ def test_embed_range_equals_frontier_embed():
             assert got.shape == (hi - lo, dims[2])
             if hi > lo:
                 assert torch.allclose(got, want[lo:hi], rtol=1e-5, atol=1e-6), float((got - want[lo:hi]).abs().max())
+
+
+def test_online_sampling_matches_table_given_same_walks():
+    """Online neighbourhoods (walker inside the forward, pinsage_model.py:142-154) drive the same engine: a table
+    precomputed with the Philox key of a plan reproduces that plan's online forward bit for bit (walks are keyed by
+    (seed, source, step), not by launch shape), and a train step runs end to end in online mode."""
+    import ps_native as nat
+    import ps_synth
+    import pinsage_model as psm
+    from ps_engine import NeighborTable, build_plan
+    from oracle import oracle
+    n_tracks, dims, L, T = 700, (64, 96, 32), 2, 6
+    g = ps_synth.make_graph(n_tracks, 100, 7000, seed=8)
+    feats = ps_synth.features(n_tracks, 64, seed=9).cuda()
+    model = psm.PinSageModel(g, n_tracks, L, dims, 200, 0.85, T, None)   # nbhds=None -> online
+    model.load_state_dict(oracle.make_params(L, dims, np.random.RandomState(3)))
+    online = model.nbhds
+    top = torch.arange(0, n_tracks, 9, device="cuda")
+    plan = build_plan(top, L, T, online, need_backward=False)
+    out_online, _ = model.engine.forward(feats, plan, keep=False)
+    ref = nat.walk_topt(g.device(), torch.arange(n_tracks), 200, 0.85, T, online._seed, want_i64=False, want_i32=True)
+    table = NeighborTable.__new__(NeighborTable)
+    table.nodes, table.w, table.n, table.Tp, table.scratch = ref["nodes_i32"], ref["weights_f32"], n_tracks, T, {}
+    plan2 = build_plan(top, L, T, table, need_backward=False)
+    out_table, _ = model.engine.forward(feats, plan2, keep=False)
+    assert torch.equal(out_online, out_table) and torch.isfinite(out_online).all()
+    seed_before = online._seed
+    batch = torch.randint(0, n_tracks, (32, 3), device="cuda")
+    loss, emb, triples = model.engine.train_step(feats, batch, 0.1, True)
+    assert online._seed != seed_before  # fresh walks per step
+    assert torch.isfinite(loss).all() and all(p.grad is not None and torch.isfinite(p.grad).all() for p in model.parameters())
