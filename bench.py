@@ -74,44 +74,63 @@ def load_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clock / throttle-reason samples during the timed region."""
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """SM clock / throttle-reason samples during the timed region, through NVML on a background thread
+    (nvidia_ml_py).  A polling `nvidia-smi -lms` child process was measured to stall kernel launches for
+    milliseconds on a fresh box (driver locks), doubling the step time of the first run; NVML queries from
+    inside the process do not.  Falls back to single nvidia-smi queries when NVML is unavailable."""
+    REASONS = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
 
-    def __init__(self, gpu_index):
-        self.tmp = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
-        self.proc = None
+    def __init__(self, gpu_index, period_s=0.1):
+        import threading
+        self.sm, self.smax, self.reasons, self.err = [], [], set(), None
+        self._stop = threading.Event()
+        self._thread = threading.Thread(target=self._run, args=(gpu_index, period_s), daemon=True)
+        self._thread.start()
+
+    def _run(self, gpu_index, period_s):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100", "-i", str(gpu_index)], stdout=self.tmp, stderr=subprocess.DEVNULL)
-        except Exception:
-            self.proc = None
+            import pynvml
+            pynvml.nvmlInit()
+            # CUDA_VISIBLE_DEVICES-safe: address the device by the PCI bus id torch reports
+            bus = torch.cuda.get_device_properties(gpu_index).pci_bus_id if hasattr(torch.cuda.get_device_properties(gpu_index), "pci_bus_id") else None
+            h = None
+            if bus is not None:
+                for i in range(pynvml.nvmlDeviceGetCount()):
+                    hh = pynvml.nvmlDeviceGetHandleByIndex(i)
+                    if int(pynvml.nvmlDeviceGetPciInfo(hh).bus) == int(bus):
+                        h = hh
+                        break
+            if h is None:
+                h = pynvml.nvmlDeviceGetHandleByIndex(gpu_index)
+            smax = pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM)
+            while not self._stop.is_set():
+                self.sm.append(float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)))
+                self.smax.append(float(smax))
+                try:
+                    r = pynvml.nvmlDeviceGetCurrentClocksEventReasons(h)
+                except Exception:
+                    r = pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                for name, bit in self.REASONS.items():
+                    if r & bit:
+                        self.reasons.add(name)
+                self._stop.wait(period_s)
+        except Exception as exc:  # NVML missing: one nvidia-smi query, outside any polling loop
+            self.err = repr(exc)
+            try:
+                out = subprocess.run(["nvidia-smi", "--query-gpu=clocks.sm,clocks.max.sm", "--format=csv,noheader,nounits", "-i", str(gpu_index)],
+                                     capture_output=True, text=True, timeout=20).stdout.strip().split(",")
+                self.sm.append(float(out[0])); self.smax.append(float(out[1]))
+            except Exception:
+                pass
 
     def stop(self):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=5)
-        except Exception:
-            self.proc.kill()
-        self.tmp.flush(); self.tmp.seek(0)
-        sm, smax, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for line in self.tmp.read().splitlines():
-            f = [x.strip() for x in line.split(",")]
-            if len(f) < 9:
-                continue
-            try:
-                sm.append(float(f[1])); smax.append(float(f[2]))
-            except ValueError:
-                continue
-            for name, val in zip(names, f[5:9]):
-                if val.lower().startswith("active"):
-                    reasons.add(name)
-        os.unlink(self.tmp.name)
-        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(smax) if smax else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+        self._stop.set()
+        self._thread.join(timeout=5)
+        out = {"sm_mhz": statistics.median(self.sm) if self.sm else None, "sm_max_mhz": max(self.smax) if self.smax else None,
+               "samples": len(self.sm), "reasons": sorted(self.reasons), "source": "nvml" if self.err is None else "nvidia-smi (single query)"}
+        if not self.sm:
+            out["reasons"] = ["clock query unavailable: " + str(self.err)]
+        return out
 
 
 def measured_traffic(tag):
@@ -299,7 +318,7 @@ def run_ours(args, wl):
 
     from collections import deque
     # batches i+1 and i+2 are sampled + planned by a worker thread on a side stream while step i runs (PinSage.train does the same)
-    pending = deque([trainer.prefetch_async(), trainer.prefetch_async()])
+    pending = deque([trainer.prefetch_async() for _ in range(3)])
 
     host = {"train": 0.0, "prefetch": 0.0}
 
@@ -354,17 +373,17 @@ def run_ours(args, wl):
     # ---- e2e: the same public call with HOST batches (pinned -> H2D -> step -> D2H of the loss) ----
     pos_cpu = positives.cpu()
     ids_cpu = torch.arange(N)
-    bufs = [torch.empty((B, 3), dtype=torch.int64).pin_memory() for _ in range(4)]
+    bufs = [torch.empty((B, 3), dtype=torch.int64).pin_memory() for _ in range(6)]
     e2e_state = {"i": 0, "pending": deque()}
 
     def e2e_prefetch():
-        buf = bufs[e2e_state["i"] % len(bufs)]; e2e_state["i"] += 1   # 4 pinned buffers: at most 3 batches are alive at once
+        buf = bufs[e2e_state["i"] % len(bufs)]; e2e_state["i"] += 1   # 6 pinned buffers: at most 4 batches are alive at once
         batch, _ = pst.sample_batch(ids_cpu, pos_cpu, B, nbhds_cpu, hard_negatives=False)  # host sampling
         buf.copy_(batch)
         return trainer.prefetch_async(buf)  # H2D of the pinned batch + planning, worker thread / side stream
 
     def e2e_step():
-        while len(e2e_state["pending"]) < 2:
+        while len(e2e_state["pending"]) < 3:
             e2e_state["pending"].append(e2e_prefetch())
         out = trainer.train_batch(e2e_state["pending"].popleft())
         e2e_state["pending"].append(e2e_prefetch())

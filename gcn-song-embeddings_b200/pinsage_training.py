@@ -10,6 +10,7 @@ wandb logging is optional (only imported when log=True).
 from __future__ import annotations
 
 import os
+import threading
 import time
 
 import torch
@@ -113,6 +114,7 @@ def sample_hard_negatives(all_ids, pos_batch, nbhds, min_rank, max_rank, referen
 
 
 _sampler_state = {"seed": None, "step": 0}
+_sampler_lock = threading.Lock()
 
 
 def sample_batch_device(all_ids, positives, batch_size):
@@ -126,10 +128,12 @@ def sample_batch_device(all_ids, positives, batch_size):
             and ps_native.sample_batch_supported(positives.shape[0], all_ids.shape[0], batch_size)):
         return None
     st = _sampler_state
-    if st["seed"] != torch.initial_seed():
-        st["seed"], st["step"] = torch.initial_seed(), 0
-    st["step"] += 1
-    return ps_native.sample_batch(positives, all_ids, all_ids.shape[0], batch_size, st["seed"], st["step"])
+    with _sampler_lock:  # several preparation threads draw batches
+        if st["seed"] != torch.initial_seed():
+            st["seed"], st["step"] = torch.initial_seed(), 0
+        st["step"] += 1
+        seed, step = st["seed"], st["step"]
+    return ps_native.sample_batch(positives, all_ids, all_ids.shape[0], batch_size, seed, step)
 
 
 def sample_batch(all_ids, positives, batch_size, nbhds, hard_negatives=True, hn_min=10, hn_max=100):
@@ -238,7 +242,10 @@ class PinSage():
         if getattr(self, "_prep_pool", None) is None:
             from concurrent.futures import ThreadPoolExecutor
             dev = torch.cuda.current_device()
-            self._prep_pool = ThreadPoolExecutor(max_workers=1, thread_name_prefix="ps_prepare",
+            # two workers, each with its own high-priority stream: a preparation is a chain of ~25 dependent launches
+            # with 3 host reads, and every link can wait behind a resident persistent GEMM of the training stream, so
+            # one worker's latency can exceed a step; two in flight keep the training thread fed
+            self._prep_pool = ThreadPoolExecutor(max_workers=2, thread_name_prefix="ps_prepare",
                                                  initializer=lambda: torch.cuda.set_device(dev))
         return self._prep_pool.submit(self.prefetch, batch)
 
@@ -294,7 +301,7 @@ class PinSage():
         """Train the model (pinsage_training.py:216-256)."""
         print("\033[0;33mTraining PinSage...\033[0m")
         from collections import deque
-        pending = deque([self.prefetch_async(), self.prefetch_async()])  # two batches in preparation at any time
+        pending = deque([self.prefetch_async() for _ in range(3)])  # three batches ahead: two in preparation, one ready
         while self.e < self.epochs:
             print(f"Training epoch {self.e+1}/{self.epochs}...")
             cur_lr = self.optimizer.param_groups[0]["lr"]

@@ -22,6 +22,7 @@ Design differences (results identical, see tests/):
 from __future__ import annotations
 
 import os
+import threading
 import time
 from dataclasses import dataclass, field
 from typing import List, Optional
@@ -162,6 +163,21 @@ def build_plan(top: torch.Tensor, n_layers: int, T: int, table: NeighborTable, n
     for l in reversed(range(n_layers)):
         n = cur.numel()
         nb, w = table.lookup(cur, T)
+        if nb.is_cuda and n > 0:
+            # native plan builder (csrc/plan.cu): dense flag map + scan for the next frontier, one radix sort for the
+            # backward transpose; a handful of launches and one host read per layer
+            nb = nb.contiguous()
+            uniq, nbz, self_rows, nz = nat.plan_layer(nb, cur, l > 0, table.n)
+            if l > 0:
+                nxt, zrows = uniq, None
+            else:
+                nxt, zrows, self_rows = None, uniq, cur.to(torch.int32)
+            lp = LayerPlan(n=n, nz=nz, self_rows=self_rows, nbz=nbz, w=w, zrows=zrows)
+            if need_backward:
+                lp.pair_q, lp.seg_off, lp.chunk_off, lp.chunk_row = nat.plan_transpose(nbz, nz)
+            plan.layers[l] = lp
+            cur = nxt
+            continue
         if l > 0:
             allv = torch.cat([nb.reshape(-1).to(torch.int64), cur])
             nxt, inv = _unique_inverse(allv, table.n, table.scratch)
@@ -176,7 +192,7 @@ def build_plan(top: torch.Tensor, n_layers: int, T: int, table: NeighborTable, n
         lp = LayerPlan(n=n, nz=nz, self_rows=self_rows, nbz=nbz, w=w, zrows=zrows)
         if need_backward:
             flat = nbz.reshape(-1)
-            skeys, order = torch.sort(flat)
+            skeys, order = torch.sort(flat, stable=True)  # q ascends inside a segment: reproducible backward sums
             lp.pair_q = order.to(torch.int32).contiguous()
             # segment starts of the sorted keys (no bincount: it reads its maximum back to the host)
             lp.seg_off = torch.searchsorted(skeys, torch.arange(nz + 1, dtype=torch.int32, device=flat.device)).to(torch.int32)
@@ -216,6 +232,7 @@ class Engine:
         self.model = model
         self._feat_src = None
         self._feat_dev = None
+        self._tls = threading.local()
 
     # ---- inputs ---------------------------------------------------------------------
     def features(self, features: torch.Tensor) -> torch.Tensor:
@@ -354,9 +371,10 @@ class Engine:
         None with `sampler` a callable that draws the batch on the side stream."""
         m = self.model
         main = torch.cuda.current_stream()
-        if getattr(self, "plan_stream", None) is None:
-            self.plan_stream = torch.cuda.Stream(priority=-1)
-        side = self.plan_stream
+        tls = self._tls
+        if getattr(tls, "plan_stream", None) is None:
+            tls.plan_stream = torch.cuda.Stream(priority=-1)  # one high-priority stream per preparing host thread
+        side = tls.plan_stream
         if batch is not None and batch.is_cuda:
             side.wait_stream(main)
         check_ids = True

@@ -57,6 +57,8 @@ _SIGNATURES = {
     "ps_count_triples": ([c_void_p, c_int64, c_int64, c_void_p, c_void_p], c_int),
     "ps_margin_loss_fwd_bwd": ([c_void_p, c_int64, c_void_p, c_int64, c_int, c_float, c_float, c_void_p, c_int64,
                                 c_void_p, c_void_p, c_int64, c_void_p], c_int),
+    "ps_plan_layer": ([c_void_p, c_int64, c_int, c_void_p, c_int, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p], c_int),
+    "ps_plan_transpose": ([c_void_p, c_int64, c_int64, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p], c_int),
     "ps_sample_batch_workspace": ([c_int], c_int64),
     "ps_sample_batch": ([c_void_p, c_int64, c_void_p, c_int64, c_int, c_uint64, c_uint64, c_void_p, c_void_p, c_int64,
                          c_void_p, c_void_p], c_int),
@@ -350,6 +352,37 @@ def margin_loss_fwd_bwd(emb, triples, margin, grad_scale, dup_counts, loss_out, 
                                        int(d), float(margin), float(grad_scale), _p(dup_counts, torch.int32), int(U),
                                        _p(loss_out, torch.float32), _p(demb, torch.float32),
                                        _ld(demb) if demb is not None else 0, _stream()))
+
+
+def plan_layer(nb, cur, with_self, n_ids):
+    """ps_plan_layer: (uniq, nbz int32 [n,T], self_rows int32 [n] or None, size) of a layer's next frontier.  uniq is int64
+    when with_self (it becomes the next layer's targets) and int32 otherwise (gather index of the Q transform).
+    One host read (the size)."""
+    _ensure_device()
+    n, T = nb.shape
+    cap = max(1, min(int(n_ids), n * T + (n if with_self else 0)))
+    u64 = torch.empty(cap, dtype=torch.int64, device="cuda") if with_self else None
+    u32 = None if with_self else torch.empty(cap, dtype=torch.int32, device="cuda")
+    nbz = torch.empty((n, T), dtype=torch.int32, device="cuda")
+    self_rows = torch.empty(n, dtype=torch.int32, device="cuda") if with_self else None
+    count = torch.empty(1, dtype=torch.int32, device="cuda")
+    check(lib().ps_plan_layer(_p(nb, torch.int32), int(n), int(T), _p(cur, torch.int64), int(with_self), int(n_ids),
+                              _p(u64), _p(u32), _p(nbz), _p(self_rows), _p(count), _stream()))
+    size = int(count)  # the layer's one host sync
+    return (u64 if with_self else u32)[:size], nbz, self_rows, size
+
+
+def plan_transpose(nbz, nz, chunk_pairs=AGG_BWD_CHUNK):
+    """ps_plan_transpose: (pair_q, seg_off, chunk_off, chunk_row) for ps_aggregate_bwd; no host sync."""
+    pairs = nbz.numel()
+    max_chunks = pairs // chunk_pairs + nz
+    pair_q = torch.empty(pairs, dtype=torch.int32, device="cuda")
+    seg_off = torch.empty(nz + 1, dtype=torch.int32, device="cuda")
+    chunk_off = torch.empty(nz + 1, dtype=torch.int32, device="cuda")
+    chunk_row = torch.empty(max(max_chunks, 1), dtype=torch.int32, device="cuda")
+    check(lib().ps_plan_transpose(_p(nbz, torch.int32), int(pairs), int(nz), int(chunk_pairs), _p(pair_q), _p(seg_off),
+                                  _p(chunk_off), _p(chunk_row), int(max_chunks), _stream()))
+    return pair_q, seg_off, chunk_off, chunk_row
 
 
 def sample_batch(positives, all_ids, n_items, B, seed, step, out=None):

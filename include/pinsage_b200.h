@@ -162,6 +162,22 @@ int ps_margin_loss_fwd_bwd(const float* emb, int64_t ld, const int32_t* triples,
                            float margin, float grad_scale, const int32_t* dup_counts, int64_t U,
                            float* loss_out, float* demb, int64_t ldd, ps_stream_t stream);
 
+/* ---- K3: frontier plans (relevant_nodes_per_layer[_precomp], pinsage_model.py:142-168) and the backward's
+ *      (target, slot) -> z-row transpose, on the device.
+ *      ps_plan_layer: nb int32 [n, T] = neighbour ids of the layer's targets cur int64 [n] (ids in [0, n_ids)).
+ *        Builds the sorted distinct set of nb (united with cur when with_self) into uniq_i64 / uniq_i32 (either may
+ *        be NULL; capacity min(n_ids, n*T + n)), nbz[q] = position of nb[q] in it, self_rows[i] = position of
+ *        cur[i] (with_self only), and writes the set's size to count_out (device int32; the caller reads it).
+ *      ps_plan_transpose: pairs q in [0, n_pairs) sorted by nbz[q] (stable) into pair_q; seg_off int32 [nz+1];
+ *        chunk_off int32 [nz+1] and chunk_row int32 [max_chunks] as ps_aggregate_bwd expects them
+ *        (max_chunks = n_pairs / chunk_pairs + nz).  Scratch is owned by the library, per (device, stream). ---- */
+int ps_plan_layer(const int32_t* nb, int64_t n, int T, const int64_t* cur, int with_self, int64_t n_ids,
+                  int64_t* uniq_i64, int32_t* uniq_i32, int32_t* nbz, int32_t* self_rows, int32_t* count_out,
+                  ps_stream_t stream);
+int ps_plan_transpose(const int32_t* nbz, int64_t n_pairs, int64_t nz, int chunk_pairs,
+                      int32_t* pair_q, int32_t* seg_off, int32_t* chunk_off, int32_t* chunk_row, int64_t max_chunks,
+                      ps_stream_t stream);
+
 /* ---- K12: one training batch drawn on the device in one launch (pinsage_training.py:53-77,
  *      easy negatives): out_batch int64 [B, 3] = (q, pos) of B distinct uniformly random rows of
  *      positives [P, 2], and one negative per row: distinct uniformly random positions of all_ids

@@ -219,3 +219,26 @@ def test_online_sampling_matches_table_given_same_walks():
     loss, emb, triples = model.engine.train_step(feats, batch, 0.1, True)
     assert online._seed != seed_before  # fresh walks per step
     assert torch.isfinite(loss).all() and all(p.grad is not None and torch.isfinite(p.grad).all() for p in model.parameters())
+
+
+@pytest.mark.parametrize("n_tracks,T,L,ntop", [(900, 5, 2, 100), (5000, 12, 3, 700), (300, 3, 2, 1)])
+def test_native_plan_builder_equals_torch_path(n_tracks, T, L, ntop):
+    """csrc/plan.cu (ps_plan_layer / ps_plan_transpose) builds exactly the plan of the framework-op path (which the
+    CPU tests pin against the reference's relevant_nodes_per_layer_precomp): frontiers, positions, the stable pair
+    order, segment offsets, work chunks and the chunk -> row map."""
+    from ps_engine import NeighborTable, build_plan
+    rng = np.random.RandomState(n_tracks)
+    nodes = torch.from_numpy(np.stack([rng.choice(n_tracks, size=T + 2, replace=False) for _ in range(n_tracks)]).astype(np.int64))
+    w = torch.from_numpy(rng.randint(1, 40, size=(n_tracks, T + 2)).astype(np.float64) / 500)
+    top = torch.from_numpy(np.sort(rng.choice(n_tracks, size=ntop, replace=False)).astype(np.int64))
+    dev = build_plan(top.cuda(), L, T, NeighborTable(w, nodes, device="cuda"), need_backward=True)
+    cpu = build_plan(top, L, T, NeighborTable(w, nodes, device="cpu"), need_backward=True)
+    for a, b in zip(dev.layers, cpu.layers):
+        assert (a.n, a.nz) == (b.n, b.nz)
+        for name in ("self_rows", "nbz", "w", "zrows", "seg_off", "pair_q", "chunk_off"):
+            x, y = getattr(a, name), getattr(b, name)
+            assert (x is None) == (y is None), name
+            if x is not None:
+                assert torch.equal(x.cpu().to(y.dtype), y), name
+        total = int(b.chunk_off[-1])
+        assert torch.equal(a.chunk_row.cpu()[:total], b.chunk_row[:total])
