@@ -219,6 +219,10 @@ def run_reference(args, wl):
         return 0
     import ps_synth
     torch.manual_seed(0)
+    try:  # torchrun exports OMP_NUM_THREADS=1; the CPU arm is entitled to every host core
+        torch.set_num_threads(max(1, len(os.sched_getaffinity(0))))
+    except Exception:
+        torch.set_num_threads(max(1, os.cpu_count() or 1))
     t_setup = time.perf_counter()
     indptr, indices, n_e = ps_synth.bipartite_csr(wl["n_tracks"], wl["n_cols"], wl["n_edges"], seed=1234, device="cpu")
     feats = ps_synth.features(wl["n_tracks"], wl["din"], seed=1, device="cpu")
@@ -313,6 +317,7 @@ def run_ours(args, wl):
     trainer.T = T; trainer.model.T = T
     trainer.batch_size = B
     trainer.online_sampling = args.sampling == "online"
+    trainer.prep_workers = args.prep_workers
     ps_dist.attach(trainer, rank, world)
     nbhds_cpu = trainer.nbhds
 
@@ -436,6 +441,7 @@ def run_ours(args, wl):
                                     "sample": f"2 timed steps (1 warm-up) of {Bc} triples (3*{Bc} nodes) on the same {N}-track graph, T={T}; {cs:.2f} s/step"}
         print(json.dumps(line), flush=True)
     ps_dist.barrier()
+    ps_dist.shutdown()
     return 0
 
 
@@ -493,6 +499,7 @@ def run_inference(args, wl):
                           "setup_s": round(setup_s, 1), "hbm_gb_allocated": round(torch.cuda.max_memory_allocated() / 1e9, 1),
                           "checksum_rank0": checksum}), flush=True)
     ps_dist.barrier()
+    ps_dist.shutdown()
     return 0
 
 
@@ -504,6 +511,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cfg3", choices=sorted(WORKLOADS))
     ap.add_argument("--mode", default="train", choices=["train", "infer"], help="infer = node-range sharded full-graph embedding (cfg4 / cfg4q)")
+    ap.add_argument("--prep-workers", type=int, default=1, help="host threads that prepare batches ahead of the training thread")
     ap.add_argument("--sampling", default="precomp", choices=["precomp", "online"],
                     help="precomp = table lookup of neighbourhoods precomputed once (the reference's default); online = the walker runs inside every step")
     ap.add_argument("--setup-steps", type=int, default=8, help="extra untimed steps before the W warm-up steps (allocator steady state)")

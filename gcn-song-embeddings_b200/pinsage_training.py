@@ -200,6 +200,7 @@ class PinSage():
         self.b_per_e = 500
 
         self.embeddings = None
+        self.prep_workers = 1          # host threads preparing batches ahead of the training thread (prefetch_async)
         self.online_sampling = False   # True: run the walker inside every step (reference's online relevant_nodes_per_layer)
         self.reference_compat = True   # duplicate-node gradient factor, hard-negative row quirk
         self.diagnostics = True        # node-feature loss + batch variance, as train_batch returns them
@@ -242,10 +243,11 @@ class PinSage():
         if getattr(self, "_prep_pool", None) is None:
             from concurrent.futures import ThreadPoolExecutor
             dev = torch.cuda.current_device()
-            # two workers, each with its own high-priority stream: a preparation is a chain of ~25 dependent launches
-            # with 3 host reads, and every link can wait behind a resident persistent GEMM of the training stream, so
-            # one worker's latency can exceed a step; two in flight keep the training thread fed
-            self._prep_pool = ThreadPoolExecutor(max_workers=2, thread_name_prefix="ps_prepare",
+            # prep_workers host threads, each with its own high-priority stream.  One is enough once the plan builder is
+            # native (a preparation is ~25 launches + 3 host reads, ~2-4 ms); more helps a single process when
+            # preparations queue behind resident persistent GEMMs, but 8 ranks x 2 workers oversubscribed the host
+            # cores of an 8-GPU box (measured: 7.49 -> 8.11 ms per step), hence the default of 1.
+            self._prep_pool = ThreadPoolExecutor(max_workers=max(1, int(getattr(self, "prep_workers", 1))), thread_name_prefix="ps_prepare",
                                                  initializer=lambda: torch.cuda.set_device(dev))
         return self._prep_pool.submit(self.prefetch, batch)
 

@@ -102,6 +102,12 @@ def max_over_ranks(value: float, device=None) -> float:
     return float(t[0])
 
 
+def shutdown():
+    """Tear the process group down (after the last collective)."""
+    if dist.is_initialized():
+        dist.destroy_process_group()
+
+
 def barrier():
     if dist.is_initialized() and dist.get_world_size() > 1:
         dist.barrier()
