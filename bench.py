@@ -280,6 +280,12 @@ def run_ours(args, wl):
         raise SystemExit("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm")
     dev = torch.device("cuda", local)
     peaks = load_peaks()
+    # The GPU arm's host work is tiny tensor ops on two Python threads; an OpenMP team per op only adds contention
+    # (measured: the e2e leg went bimodal, 7.3 / 12 ms per step).  The CPU baseline gets all cores back below.
+    host_threads = torch.get_num_threads()
+    torch.set_num_threads(1)
+    allowed_cpus = os.sched_getaffinity(0)
+    numa_note = ps_dist.bind_to_gpu_cpus(local)
     if args.tc_waves:
         ps_native.lib().ps_gemm_tc_waves(args.tc_waves)
     torch.manual_seed(1000 + rank)
@@ -378,23 +384,47 @@ def run_ours(args, wl):
     # ---- e2e: the same public call with HOST batches (pinned -> H2D -> step -> D2H of the loss) ----
     pos_cpu = positives.cpu()
     ids_cpu = torch.arange(N)
-    bufs = [torch.empty((B, 3), dtype=torch.int64).pin_memory() for _ in range(6)]
-    e2e_state = {"i": 0, "pending": deque()}
+    import itertools
+    import threading
+    bufs = [torch.empty((B, 3), dtype=torch.int64).pin_memory() for _ in range(8)]  # at most 4 batches are alive at once
+    buf_ids, buf_lock = itertools.count(), threading.Lock()
+    pending_e2e = deque()
 
-    def e2e_prefetch():
-        buf = bufs[e2e_state["i"] % len(bufs)]; e2e_state["i"] += 1   # 6 pinned buffers: at most 4 batches are alive at once
-        batch, _ = pst.sample_batch(ids_cpu, pos_cpu, B, nbhds_cpu, hard_negatives=False)  # host sampling
-        buf.copy_(batch)
-        return trainer.prefetch_async(buf)  # H2D of the pinned batch + planning, worker thread / side stream
+    pos_np = pos_cpu.numpy()
+    host_rng = np.random.default_rng(4242 + rank)
+
+    def host_sample_numpy():
+        """The law of pst.sample_batch with easy negatives (B distinct positive rows; B distinct negatives outside the
+        pairs), as ~10 numpy calls: the torch-CPU version costs the preparation thread 1-3 ms of small-op dispatch."""
+        rows = np.empty(0, dtype=np.int64)
+        while rows.size < B:
+            cand = np.concatenate([rows, host_rng.integers(0, pos_np.shape[0], size=B + B // 4 + 16)])
+            _, first = np.unique(cand, return_index=True)
+            rows = cand[np.sort(first)]
+        pairs = pos_np[rows[:B]]
+        pos_nodes = np.unique(pairs)
+        neg = np.empty(0, dtype=np.int64)
+        while neg.size < B:
+            cand = host_rng.integers(0, N, size=2 * B)
+            cand = np.concatenate([neg, cand[~np.isin(cand, pos_nodes)]])
+            _, first = np.unique(cand, return_index=True)
+            neg = cand[np.sort(first)]
+        return np.concatenate([pairs, neg[:B, None]], axis=1)
+
+    def host_batch():  # runs on the preparation worker: host sampling into a pinned buffer (H2D happens in prefetch)
+        with buf_lock:
+            buf = bufs[next(buf_ids) % len(bufs)]
+        buf.copy_(torch.from_numpy(host_sample_numpy()))
+        return buf
 
     def e2e_step():
-        while len(e2e_state["pending"]) < 3:
-            e2e_state["pending"].append(e2e_prefetch())
-        out = trainer.train_batch(e2e_state["pending"].popleft())
-        e2e_state["pending"].append(e2e_prefetch())
+        while len(pending_e2e) < 3:
+            pending_e2e.append(trainer.prefetch_async(host_sampler=host_batch))
+        out = trainer.train_batch(pending_e2e.popleft())
+        pending_e2e.append(trainer.prefetch_async(host_sampler=host_batch))
         return float(out[0])  # D2H read of the step's result
 
-    for _ in range(args.warmup):
+    for _ in range(args.setup_steps // 2 + args.warmup):  # untimed: allocator steady state for the host-batch path too
         e2e_step()
     torch.cuda.synchronize(); ps_dist.barrier()
     w0 = time.perf_counter()
@@ -426,7 +456,8 @@ def run_ours(args, wl):
                      "sources": N, "n_hops": 500, "alpha": 0.85, "T": 100, "ms": round(walk_ms, 3),
                      "algorithmic_gbs": round(walk_steps_per_s * 28 / 1e9, 2),
                      "frac_of_hbm": round(walk_steps_per_s * 28 / 1e9 / peaks["hbm_gbs"], 4)},
-            "final_loss": final_loss, "host_ms_per_step": host_ms, "cudaMallocs_in_timed_region": dev_allocs}
+            "final_loss": final_loss, "host_ms_per_step": host_ms, "cudaMallocs_in_timed_region": dev_allocs,
+            "host_placement": numa_note}
     import ps_engine
     if ps_engine._PREP_TIMING is not None and ps_engine._PREP_TIMING["n"]:
         t = ps_engine._PREP_TIMING
@@ -434,6 +465,8 @@ def run_ours(args, wl):
     if rank == 0:
         line["roofline"] = roofline_from_profile(prof, args.steps, peaks)
         if world == 1 and not args.no_cpu_baseline:
+            os.sched_setaffinity(0, allowed_cpus)
+            torch.set_num_threads(host_threads)
             Bc = wl["ref_batch"]
             cpu_batches = [pst.sample_batch(ids_cpu, pos_cpu, Bc, nbhds_cpu, hard_negatives=False)[0].numpy() for _ in range(3)]
             cv, cs = cpu_train_baseline(feats.cpu(), nbhds_cpu, (din, 512, 128), L, T, cpu_batches, warmup=1)

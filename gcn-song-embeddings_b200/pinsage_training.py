@@ -200,6 +200,7 @@ class PinSage():
         self.b_per_e = 500
 
         self.embeddings = None
+        self.max_steps_in_flight = 1   # device queue depth in steps (None / 0 = unlimited)
         self.prep_workers = 1          # host threads preparing batches ahead of the training thread (prefetch_async)
         self.online_sampling = False   # True: run the walker inside every step (reference's online relevant_nodes_per_layer)
         self.reference_compat = True   # duplicate-node gradient factor, hard-negative row quirk
@@ -236,7 +237,7 @@ class PinSage():
             self._pos_src = self.positives
         return self._pos_dev
 
-    def prefetch_async(self, batch=None):
+    def prefetch_async(self, batch=None, host_sampler=None):
         """prefetch() on a background host thread: returns a Future whose result train_batch() accepts.  The batch
         preparation holds ~100 small launches and 3 host syncs (the sizes of the three frontiers); with two batches
         in flight on the worker the training thread never waits for them, it only enqueues the step's kernels."""
@@ -249,6 +250,8 @@ class PinSage():
             # cores of an 8-GPU box (measured: 7.49 -> 8.11 ms per step), hence the default of 1.
             self._prep_pool = ThreadPoolExecutor(max_workers=max(1, int(getattr(self, "prep_workers", 1))), thread_name_prefix="ps_prepare",
                                                  initializer=lambda: torch.cuda.set_device(dev))
+        if host_sampler is not None:  # the worker also draws the batch on the host (returns an int64 [B,3] host tensor)
+            return self._prep_pool.submit(lambda: self.prefetch(host_sampler()))
         return self._prep_pool.submit(self.prefetch, batch)
 
     def prefetch(self, batch=None):
@@ -284,10 +287,24 @@ class PinSage():
         prep = batch if hasattr(batch, "plan") else self.prefetch(batch)
         batch = prep.batch
         feats = self._feats()
+        # At most `max_steps_in_flight` steps queued on the device.  With an always-full training queue the batch
+        # preparation (a chain of small dependent kernels on another stream) only advances one kernel per GEMM boundary
+        # -- every SM holds a persistent GEMM CTA -- and a preparation can take 2-3 steps (measured: 7.2 -> 12-19 ms
+        # per step, bimodal).  Waiting for the previous step before enqueuing the next one leaves the device to the
+        # preparation stream at every step boundary and costs ~2 % when everything is on time.
+        done = getattr(self, "_steps_in_flight", None)
+        if done is None:
+            from collections import deque
+            done = self._steps_in_flight = deque()
+        while self.max_steps_in_flight and len(done) >= self.max_steps_in_flight:
+            done.popleft().synchronize()
         loss, emb, triples = self.model.engine.train_step(feats, prep, self.margin, self.reference_compat)
         if self._grad_sync is not None:
             self._grad_sync()
         self.optimizer.step()
+        ev = torch.cuda.Event()
+        ev.record()
+        done.append(ev)
         if self.diagnostics:
             with torch.no_grad():
                 norm = F.normalize

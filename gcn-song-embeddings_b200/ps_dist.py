@@ -31,6 +31,39 @@ def init_from_env(backend=None):
     return rank, world, local
 
 
+def bind_to_gpu_cpus(device_index: int):
+    """Pin this process to the CPU cores NVML reports as local to the GPU (its NUMA node), intersected with the
+    cores the container allows.  The step is a chain of host <-> device round trips (batch preparation, the per-step
+    loss read); a process that lands on the far NUMA node pays for each of them.  Returns a short description."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = None
+        try:
+            bus = torch.cuda.get_device_properties(device_index).pci_bus_id
+            for i in range(pynvml.nvmlDeviceGetCount()):
+                hh = pynvml.nvmlDeviceGetHandleByIndex(i)
+                if int(pynvml.nvmlDeviceGetPciInfo(hh).bus) == int(bus):
+                    h = hh
+                    break
+        except Exception:
+            h = None
+        if h is None:
+            h = pynvml.nvmlDeviceGetHandleByIndex(device_index)
+        n_words = (os.cpu_count() + 63) // 64
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, n_words)
+        local = {64 * w + b for w, word in enumerate(words) for b in range(64) if (int(word) >> b) & 1}
+        allowed = os.sched_getaffinity(0)
+        target = local & allowed
+        if not target:
+            return f"not bound: none of the {len(local)} GPU-local cores is among the {len(allowed)} allowed ones"
+        if target != allowed:
+            os.sched_setaffinity(0, target)
+        return f"bound to {len(target)} GPU-local cores (of {len(allowed)} allowed)"
+    except Exception as exc:
+        return f"not bound: {exc!r}"
+
+
 def allreduce_mean_(flat: torch.Tensor, world_size: int):
     """In-place mean of a flat gradient buffer over all ranks."""
     if world_size > 1:
