@@ -2,21 +2,28 @@
 """Benchmark of the PinSage hot path (BASELINE.json metric: train nodes/sec,
 sample+fwd+bwd; walk steps/sec).
 
-    python bench.py [--gpus N --steps K --warmup W] [--impl reference] [--workload cfg3|micro]
+    python bench.py [--gpus N --steps K --warmup W] [--impl reference] [--workload cfg3|cfg1|cfg2|micro]
+                    [--sampling precomp|online] [--mode infer --workload cfg4|cfg4q [--exchange]]
 
 Our arm (default): the drop-in trainer `pinsage_training.PinSage` on the synthetic
 1 M tracks / 200 k playlists / 40 M edges graph of BASELINE.json configs[2] (256-d
 features, 2 layers, T=50, batch 1024 per GPU, precomputed neighbourhoods as the reference
 does by default).  One step = sample a batch + PinSage.train_batch (shared-frontier
-forward, max-margin loss, backward, Adam).  `value` is timed with the batch sampled on the
-device (everything resident in HBM); `e2e` goes through the same public call with HOST
-batches: host sampling -> pinned buffer -> H2D -> step -> D2H of the loss, every step.
+forward, max-margin loss, backward, Adam); batches are prepared three ahead by the trainer's
+worker thread (PinSage.prefetch_async), as PinSage.train() does.  `value` is timed with the
+batch sampled on the device (everything resident in HBM); `e2e` goes through the same public
+call with HOST batches: host sampling -> pinned buffer -> H2D -> step -> D2H of the loss,
+every step.  `roofline`: CUDA events around every ABI call of the timed region, the kernel
+with the largest share reported against its bound (`traffic` from the committed ncu capture).
 Multi-GPU: one process per GPU (torchrun), data parallel, one NCCL allreduce of the flat
 gradient per step; weak scaling (batch 1024 per GPU).
 
 Reference arm (--impl reference): the CPU oracle port of the reference's train step
 (oracle/oracle.py, full-table clones and dense autograd included) on the box's host cores,
 same graph generator / config, bounded sample (small batch) per step.
+
+--mode infer: node-range sharded full-graph embedding (BASELINE.json configs[3]); not the
+headline line.
 """
 from __future__ import annotations
 
@@ -486,7 +493,6 @@ def run_inference(args, wl):
     import ps_native
     import ps_synth
     import pinsage_model as psm
-    from oracle import oracle
     rank, world, local = ps_dist.init_from_env()
     N, C, din, T, L = wl["n_tracks"], wl["n_cols"], wl["din"], wl["T"], wl["n_layers"]
     t0 = time.perf_counter()
@@ -504,8 +510,8 @@ def run_inference(args, wl):
     table = NeighborTable.__new__(NeighborTable)
     table.nodes, table.w, table.n, table.Tp, table.scratch = out["nodes_i32"], out["weights_f32"], N, T, {}
     dims = (din, 512, 128)
+    torch.manual_seed(0)  # the same random-init weights (xavier, bias 0.3: the model's own initialiser) on every rank
     model = psm.PinSageModel(g, N, L, dims, 500, 0.85, T, table)
-    model.load_state_dict(oracle.make_params(L, dims, np.random.RandomState(0)))  # seeded xavier weights, bias 0.3
 
     class _T:  # the two attributes embed_shard reads
         pass
