@@ -88,26 +88,32 @@ def get_knn_dict(models, g, ids, train_pos, test_pos, features, save_dir, k=None
 
 
 def low_degree_accuracy(knn_mat, g, test_positives, K, degree_thr=1, acc_func=mrr):
-    """Accuracy restricted to test pairs whose query has at most degree_thr collections
-    (eval.py:376-389)."""
-    deg = g.in_degrees()
+    """Accuracy restricted to test pairs whose query has at most degree_thr collections; 0 when no node
+    qualifies (eval.py:376-389)."""
+    deg = torch.as_tensor(g.in_degrees())[: knn_mat.shape[0]]
+    if int((deg <= degree_thr).sum()) == 0:
+        return 0
     tp = torch.as_tensor(test_positives)
-    keep = deg[tp[:, 0]] <= degree_thr
-    if int(keep.sum()) == 0:
-        return float("nan")
-    return acc_func(knn_mat, tp[keep], K)
+    return acc_func(knn_mat, tp[deg[tp[:, 0]] <= degree_thr], K)
+
+
+def low_co_accuracy(knn_mat, g, test_positives, K, co_thr=1, acc_func=mrr):
+    """Accuracy restricted to test pairs whose query occurs in at most co_thr test pairs (eval.py:391-406: the row
+    sums of the track-track co-occurrence count matrix of the test positives are the per-query pair counts)."""
+    tp = torch.as_tensor(test_positives)
+    co_counts = torch.bincount(tp[:, 0], minlength=knn_mat.shape[0])
+    return acc_func(knn_mat, tp[co_counts[tp[:, 0]] <= co_thr], K)
 
 
 def compute_results_table(knn_dict, test_positives, g, times=True, degree_thr=1):
-    """hit-rate@10/100/500, MRR@1000 and low-degree MRR per model (eval.py:413-443; the
-    low-co-occurrence column needs the track-track co-occurrence matrix of the other
-    baselines and is not reproduced)."""
+    """hit-rate@10/100/500, MRR@1000, low-degree and low-co-occurrence MRR per model (eval.py:413-443)."""
     results = {}
     for model in knn_dict:
         _, knn_mat = knn_dict[model]
         row = {f"hr (k={k})": hit_rate(knn_mat, test_positives, k) for k in (10, 100, 500)}
         row["mrr"] = mrr(knn_mat, test_positives, 1000, 1)
         row["low-degree accuracy"] = low_degree_accuracy(knn_mat, g, test_positives, 1000, degree_thr=degree_thr, acc_func=mrr)
+        row["low-co accuracy"] = low_co_accuracy(knn_mat, g, test_positives, 1000, co_thr=1, acc_func=mrr)
         if times and hasattr(knn_dict, "get_times"):
             row["t (train)"], row["t (emb)"], row["t (knn)"] = knn_dict.get_times(model)
         results[model] = row

@@ -269,6 +269,50 @@ def gen_dataset():
     print("dataset", features.shape, pos.shape, train.shape, test.shape)
 
 
+def gen_results_table():
+    """The reference's compute_results_table (eval.py:413-443) on a small graph + random kNN lists: HR@10/100/500,
+    MRR@1000, low-degree and low-co-occurrence MRR."""
+    import eval as ref_eval  # noqa  (reference eval.py)
+    rng = np.random.RandomState(77)
+    n_tracks, n_cols = 120, 30
+    from_nodes, to_nodes = synth_bipartite(n_tracks, n_cols, 3, rng)
+    g = dgl.DGLGraph(); g.add_nodes(n_tracks + n_cols); g.add_edges(from_nodes, to_nodes)
+    knn = torch.from_numpy(np.stack([rng.permutation(n_tracks)[:60] for _ in range(n_tracks)]).astype(np.int64))
+    test_pos = torch.from_numpy(rng.randint(0, n_tracks, size=(400, 2)).astype(np.int64))
+    out = {"n_tracks": np.int64(n_tracks), "n_cols": np.int64(n_cols), "from": np.asarray(from_nodes), "to": np.asarray(to_nodes),
+           "knn": knn.numpy(), "test_pos": test_pos.numpy()}
+    for thr in (1, 3):
+        table = ref_eval.compute_results_table({"m": (None, knn)}, test_pos, g, times=False, degree_thr=thr)
+        for col in table.columns:
+            out[f"thr{thr}/{col}"] = np.float64(table.loc["m", col])
+    np.savez_compressed(os.path.join(OUT, "results_table.npz"), **out)
+    print("results_table", {k: float(v) for k, v in out.items() if k.startswith("thr")})
+
+
+def gen_batches():
+    """The reference's batch construction (pinsage_training.py:53-103) under fixed torch seeds: easy negatives, hard
+    negatives (with its row-gather quirk, :84) and batch_variance.  The drop-in reproduces these draws exactly on the
+    host for sizes below its large-graph thresholds (same torch RNG calls)."""
+    rng = np.random.RandomState(11)
+    n, P, B = 300, 500, 32
+    positives = torch.from_numpy(rng.randint(0, n, size=(P, 2)).astype(np.int64))
+    w, nodes = random_nbhds(n, 100, rng)
+    nbhds = (torch.from_numpy(w), torch.from_numpy(nodes))
+    all_ids = torch.arange(n, dtype=torch.int64)
+    out = {"n": np.int64(n), "B": np.int64(B), "positives": positives.numpy(), "nb_nodes": nodes}
+    for seed in (0, 1, 2):
+        torch.manual_seed(seed)
+        b, ns = ref_pst.sample_batch(all_ids, positives, B, nbhds, hard_negatives=False)
+        out[f"easy{seed}"] = b.numpy(); out[f"easy{seed}_nodeset"] = ns.numpy()
+        torch.manual_seed(seed)
+        b, ns = ref_pst.sample_batch(all_ids, positives, B, nbhds, hard_negatives=True, hn_min=10, hn_max=100)
+        out[f"hard{seed}"] = b.numpy(); out[f"hard{seed}_nodeset"] = ns.numpy()
+    h = torch.tensor(rng.standard_normal((16, 8)), dtype=torch.float32)
+    out["var_h"] = h.numpy(); out["var"] = ref_pst.batch_variance(h).numpy()
+    np.savez_compressed(os.path.join(OUT, "batches.npz"), **out)
+    print("batches", out["easy0"][:2].tolist(), out["hard0"][:2].tolist())
+
+
 def gen_eval_parity():
     """BASELINE.json configs[1] stand-in (the real dataset_final_intersect is not in the checkout): the REFERENCE
     end to end on a small synthetic dataset in its own on-disk schema -- SpotifyGraph loader, 70/30 split,
@@ -332,7 +376,7 @@ def gen_eval_parity():
 
 
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["walk_topt", "walk_dist", "frontier", "model", "train_steps", "loss", "metrics_knn", "dataset", "eval_parity"]
+    which = sys.argv[1:] or ["walk_topt", "walk_dist", "frontier", "model", "train_steps", "loss", "metrics_knn", "dataset", "eval_parity", "results_table", "batches"]
     if "walk_topt" in which: gen_walk_topt()
     if "walk_dist" in which: gen_walk_dist()
     if "frontier" in which: gen_frontier()
@@ -345,3 +389,5 @@ if __name__ == "__main__":
     if "metrics_knn" in which: gen_metrics_knn()
     if "dataset" in which: gen_dataset()
     if "eval_parity" in which: gen_eval_parity()
+    if "results_table" in which: gen_results_table()
+    if "batches" in which: gen_batches()

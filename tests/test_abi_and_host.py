@@ -208,6 +208,20 @@ def test_spotify_graph_matches_reference_loader(golden, tmp_path):
     assert np.array_equal(train.numpy(), g["train"]) and np.array_equal(test.numpy(), g["test"])
 
 
+def test_results_table_matches_reference(golden):
+    """eval.compute_results_table == the reference's (eval.py:413-443) on its own output: HR@10/100/500, MRR@1000,
+    low-degree MRR (two thresholds) and low-co-occurrence MRR."""
+    import eval as ev
+    from ps_graph import PSGraph
+    g = golden("results_table")
+    graph = PSGraph.from_edges(g["from"], g["to"], int(g["n_tracks"]), int(g["n_cols"]))
+    kd = ev.KnnDict(); kd["m"] = (None, torch.from_numpy(g["knn"]))
+    for thr in (1, 3):
+        table = ev.compute_results_table(kd, torch.from_numpy(g["test_pos"]), graph, times=False, degree_thr=thr)
+        for col in ("hr (k=10)", "hr (k=100)", "hr (k=500)", "mrr", "low-degree accuracy", "low-co accuracy"):
+            assert float(table.loc["m", col]) == pytest.approx(float(g[f"thr{thr}/{col}"]), abs=1e-12), (thr, col)
+
+
 def test_results_table_host_logic():
     import eval as ev
     from ps_graph import PSGraph
@@ -220,3 +234,26 @@ def test_results_table_host_logic():
     assert table.loc["m", "mrr"] == pytest.approx((1 / 2 + 1 / 3 + 1 / 3 + 1 / 1000) / 4)
     assert table.loc["m", "low-degree accuracy"] == pytest.approx((1 / 3 + 1 / 3 + 1 / 1000) / 3)  # node 0 has degree 2
     assert table.loc["m", "t (knn)"] == 3.0
+
+
+def test_batch_construction_equals_reference_draws(golden):
+    """sample_batch (easy and hard negatives, incl. the reference's row-gather quirk under reference_compat) and
+    batch_variance reproduce the reference's outputs under the same torch seed (pinsage_training.py:53-103)."""
+    import pinsage_training as pst
+    g = golden("batches")
+    n, B = int(g["n"]), int(g["B"])
+    positives = torch.from_numpy(g["positives"]); all_ids = torch.arange(n, dtype=torch.int64)
+    nbhds = (None, torch.from_numpy(g["nb_nodes"]))
+    for seed in (0, 1, 2):
+        torch.manual_seed(seed)
+        b, ns = pst.sample_batch(all_ids, positives, B, nbhds, hard_negatives=False)
+        assert np.array_equal(b.numpy(), g[f"easy{seed}"]) and np.array_equal(ns.numpy(), g[f"easy{seed}_nodeset"])
+        torch.manual_seed(seed)
+        b, ns = pst.sample_batch(all_ids, positives, B, nbhds, hard_negatives=True, hn_min=10, hn_max=100)
+        assert np.array_equal(b.numpy(), g[f"hard{seed}"]) and np.array_equal(ns.numpy(), g[f"hard{seed}_nodeset"])
+    # the fixed variant gathers the queries' own rows
+    torch.manual_seed(0)
+    pos_batch = pst.sample_positives_with_rep(positives, B)
+    fixed, _ = pst.sample_hard_negatives(all_ids, pos_batch, nbhds, 10, 100, reference_compat=False)
+    assert all(int(fixed[i, 2]) in g["nb_nodes"][int(fixed[i, 0]), 10:100] for i in range(B))
+    assert float(pst.batch_variance(torch.from_numpy(g["var_h"]))) == pytest.approx(float(g["var"]), rel=1e-6)
