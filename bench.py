@@ -295,6 +295,8 @@ def run_ours(args, wl):
     numa_note = ps_dist.bind_to_gpu_cpus(local)
     if args.tc_waves:
         ps_native.lib().ps_gemm_tc_waves(args.tc_waves)
+    if args.gemm_reserve_sms:
+        ps_native.lib().ps_gemm_tc_reserve_sms(args.gemm_reserve_sms)
     torch.manual_seed(1000 + rank)
     N, C, din, T, B, L = wl["n_tracks"], wl["n_cols"], wl["din"], wl["T"], wl["batch"], wl["n_layers"]
 
@@ -557,6 +559,7 @@ def main():
     ap.add_argument("--exchange", action="store_true", help="infer mode: all-gather layer outputs instead of recomputing the closure")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--tc-waves", type=int, default=0, help="override ps_gemm_tc_waves (development)")
+    ap.add_argument("--gemm-reserve-sms", type=int, default=0, help="ps_gemm_tc_reserve_sms: SMs the persistent GEMMs leave free (development)")
     ap.add_argument("--torch-profile", default=None, help="write a torch.profiler kernel table of 3 extra steps here")
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]

@@ -687,6 +687,7 @@ __global__ void __launch_bounds__(256) pack_b_kernel(const float* __restrict__ Q
 // call on that stream (stream order makes the reuse safe; cudaFree of an outgrown buffer waits for its readers).
 // cudaMallocAsync per call was measured to stall the host inside the training step.
 static int g_tc_waves = 1;
+static int g_tc_reserve = 0;
 
 struct PackSlot { int dev; cudaStream_t stream; void* ptr; size_t bytes; };
 static PackSlot g_pack_slots[16] = {};
@@ -741,7 +742,8 @@ int launch_tc(TcArgs a, int q_kmajor, cudaStream_t stream) {
     // after 1/g_tc_waves of its SM's share and a pending higher-priority CTA (the side-stream batch preparation of the
     // next training step) gets the SM within a fraction of the GEMM instead of after all of it.
     const int64_t total = a.mt * a.nt * a.zs;
-    int64_t grid64 = total < sms ? total : sms;
+    const int64_t usable = sms - g_tc_reserve > 1 ? sms - g_tc_reserve : 1;  // SMs left free for other streams
+    int64_t grid64 = total < usable ? total : usable;
     if (g_tc_waves > 1 && total >= static_cast<int64_t>(sms) * 8 * g_tc_waves) grid64 = static_cast<int64_t>(sms) * g_tc_waves;
     const unsigned grid = static_cast<unsigned>(grid64);
     kern<<<grid, kThreads, smem, stream>>>(a);
@@ -751,6 +753,7 @@ int launch_tc(TcArgs a, int q_kmajor, cudaStream_t stream) {
 
 }  // namespace
 
+extern "C" int ps_gemm_tc_reserve_sms(int n) { const int old = g_tc_reserve; if (n >= 0 && n <= 64) g_tc_reserve = n; return old; }
 extern "C" int ps_gemm_tc_waves(int waves) { const int old = g_tc_waves; if (waves >= 1 && waves <= 64) g_tc_waves = waves; return old; }
 static bool g_tc_pack = true;
 extern "C" int ps_gemm_tc_pack(int on) { const int old = g_tc_pack; if (on == 0 || on == 1) g_tc_pack = on != 0; return old; }

@@ -38,6 +38,7 @@ _SIGNATURES = {
     "ps_gemm_mask_supported": ([c_int64, c_int64, c_int64], c_int),
     "ps_gemm_tc_pack": ([c_int], c_int),
     "ps_gemm_tc_waves": ([c_int], c_int),
+    "ps_gemm_tc_reserve_sms": ([c_int], c_int),
     "ps_graph_create": ([c_void_p, c_void_p, c_int64, c_int64, c_int64, ctypes.POINTER(c_void_p), c_void_p], c_int),
     "ps_graph_destroy": ([c_void_p], c_int),
     "ps_walk_topt": ([c_void_p, c_void_p, c_int64, c_int, c_double, c_int, c_int, c_uint64,

@@ -106,6 +106,9 @@ int ps_gemm_tc_pack(int on);
 /* Tuning knob: large tensor-core GEMMs launch waves x SMs persistent CTAs (default 1 = one CTA per SM; measured best on cfg3), so an SM is handed to a
  * pending higher-priority stream after 1/waves of the GEMM.  1 = one CTA per SM.  Returns the previous value. */
 int ps_gemm_tc_waves(int waves);
+/* Tuning knob: the persistent tensor-core GEMMs leave n SMs free (default 0) so that kernels of other streams (the
+ * batch preparation of the next training step) never wait for a GEMM to retire.  Returns the previous value. */
+int ps_gemm_tc_reserve_sms(int n);
 
 /* ---- K4+K6: neighbour gather + importance-weighted mean fused with the concat
  *      (pinsage_model.py:195-197,202,208):
