@@ -23,6 +23,7 @@
 // 208-210, 259).
 #include "common.cuh"
 #include "../../include/pinsage_b200.h"
+#include <mutex>
 
 namespace {
 
@@ -692,7 +693,10 @@ static int g_tc_reserve = 0;
 struct PackSlot { int dev; cudaStream_t stream; void* ptr; size_t bytes; };
 static PackSlot g_pack_slots[16] = {};
 
+static std::mutex g_pack_mutex;
+
 static int pack_scratch(cudaStream_t stream, size_t bytes, void** out) {
+    std::lock_guard<std::mutex> lock(g_pack_mutex);  // several host threads may run GEMMs (one stream each)
     int dev = 0;
     PS_CUDA_CHECK(cudaGetDevice(&dev));
     PackSlot* slot = nullptr;
