@@ -97,6 +97,23 @@ def shard_range(n: int, rank: int, world_size: int):
     return lo, min(n, lo + per)
 
 
+def all_gather_rows_(table: torch.Tensor, lo: int, hi: int, world_size: int):
+    """Fill the rows of `table` [n, d] that other ranks own: this rank holds rows [lo, hi) = shard_range(n, rank,
+    world_size); afterwards every rank holds the full table.  One all_gather_into_tensor of equal-sized (padded)
+    shards; with even shards the gather writes straight into the table."""
+    n, d = table.shape
+    per = -(-n // world_size)
+    if per * world_size == n:
+        dist.all_gather_into_tensor(table, table[lo:hi].clone())
+        return table
+    mine = torch.zeros((per, d), dtype=table.dtype, device=table.device)
+    mine[: hi - lo] = table[lo:hi]
+    full = torch.empty((per * world_size, d), dtype=table.dtype, device=table.device)
+    dist.all_gather_into_tensor(full, mine)
+    table.copy_(full[:n])
+    return table
+
+
 def embed_shard(trainer, rank: int = None, world_size: int = None, chunk: int = 1 << 18, stats=None, exchange: bool = False):
     """Node-range sharded full-graph inference (BASELINE.json configs[3]): this rank's rows
     [lo, hi) of the embedding matrix, float32 on the device.  Graph, features and neighbourhood table are replicated.
@@ -110,19 +127,7 @@ def embed_shard(trainer, rank: int = None, world_size: int = None, chunk: int = 
     trainer.model.eval()
     gather = None
     if exchange and world_size > 1:
-        per = -(-trainer.n // world_size)
-
-        def gather(table, lo_, hi_):
-            # equal-sized padded shards so one all_gather_into_tensor moves everything
-            n, d = table.shape
-            if per * world_size == n:  # even shards: gather straight into the table
-                dist.all_gather_into_tensor(table, table[lo_:hi_].clone())
-                return
-            mine = torch.zeros((per, d), dtype=table.dtype, device=table.device)
-            mine[: hi_ - lo_] = table[lo_:hi_]
-            full = torch.empty((per * world_size, d), dtype=table.dtype, device=table.device)
-            dist.all_gather_into_tensor(full, mine)
-            table.copy_(full[:n])
+        gather = lambda table, lo_, hi_: all_gather_rows_(table, lo_, hi_, world_size)
     emb = trainer.model.engine.embed_range(trainer._feats(), lo, hi, chunk=chunk, stats=stats, gather_layer=gather)
     return lo, hi, emb
 

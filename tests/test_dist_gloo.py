@@ -53,6 +53,14 @@ def _worker(rank, world, port, out):
     lo, hi = ps_dist.shard_range(1001, rank, world)
     sizes = torch.tensor([hi - lo]); dist.all_reduce(sizes)
     assert int(sizes) == 1001 and (lo == 0 if rank == 0 else lo == 501)
+    # layer-output exchange of the sharded inference: even and ragged shards
+    for n in (1000, 1001, 7):
+        lo, hi = ps_dist.shard_range(n, rank, world)
+        want = torch.arange(n * 3, dtype=torch.float32).view(n, 3)
+        table = torch.full((n, 3), -1.0)
+        table[lo:hi] = want[lo:hi]
+        ps_dist.all_gather_rows_(table, lo, hi, world)
+        assert torch.equal(table, want), n
     ps_dist.barrier()
     out.put(rank)
     dist.destroy_process_group()
