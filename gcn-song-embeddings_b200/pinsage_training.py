@@ -254,6 +254,12 @@ class PinSage():
             return self._prep_pool.submit(lambda: self.prefetch(host_sampler()))
         return self._prep_pool.submit(self.prefetch, batch)
 
+    def close(self):
+        """Stop the batch-preparation worker(s) (idempotent; a later prefetch_async() starts new ones)."""
+        pool, self._prep_pool = getattr(self, "_prep_pool", None), None
+        if pool is not None:
+            pool.shutdown(wait=True, cancel_futures=True)
+
     def prefetch(self, batch=None):
         """Start preparing the NEXT batch (frontier plans, backward transposes: index work that does not depend
         on the weights) on a side stream while the current step's kernels run.  With batch=None a batch is drawn
@@ -344,6 +350,8 @@ class PinSage():
             self.b = 0
             self.e += 1
             self.scheduler.step()
+        for fut in pending:  # batches prepared ahead but not needed any more
+            fut.cancel()
 
     def embed(self, ids=None, bsize=None):
         """Node embeddings, optionally only for `ids` / in `bsize` batches
