@@ -53,10 +53,12 @@ int scratch(cudaStream_t stream, int slot_id, size_t bytes, void** out) {
 }
 
 __global__ void mark_kernel(const int32_t* __restrict__ nb, int64_t n_nb, const int64_t* __restrict__ cur, int64_t n_cur,
-                            int with_self, int32_t* __restrict__ flag) {
+                            int with_self, int64_t n_ids, int32_t* __restrict__ flag) {
     const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-    if (i < n_nb) flag[nb[i]] = 1;
-    if (with_self && i < n_cur) flag[cur[i]] = 1;
+    // ids are range-checked when the table is built (NeighborTable._sanitize); an id that is out of range anyway is
+    // skipped here instead of written out of bounds
+    if (i < n_nb && static_cast<uint32_t>(nb[i]) < static_cast<uint32_t>(n_ids)) flag[nb[i]] = 1;
+    if (with_self && i < n_cur && static_cast<uint64_t>(cur[i]) < static_cast<uint64_t>(n_ids)) flag[cur[i]] = 1;
 }
 
 __global__ void compact_kernel(const int32_t* __restrict__ flag, const int32_t* __restrict__ pos, int64_t n_ids,
@@ -70,11 +72,12 @@ __global__ void compact_kernel(const int32_t* __restrict__ flag, const int32_t* 
 }
 
 __global__ void inverse_kernel(const int32_t* __restrict__ pos, const int32_t* __restrict__ nb, int64_t n_nb,
-                               const int64_t* __restrict__ cur, int64_t n_cur, int with_self,
+                               const int64_t* __restrict__ cur, int64_t n_cur, int with_self, int64_t n_ids,
                                int32_t* __restrict__ nbz, int32_t* __restrict__ self_rows) {
     const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-    if (i < n_nb) nbz[i] = pos[nb[i]];
-    if (with_self && self_rows != nullptr && i < n_cur) self_rows[i] = pos[cur[i]];
+    if (i < n_nb) nbz[i] = static_cast<uint32_t>(nb[i]) < static_cast<uint32_t>(n_ids) ? pos[nb[i]] : 0;
+    if (with_self && self_rows != nullptr && i < n_cur)
+        self_rows[i] = static_cast<uint64_t>(cur[i]) < static_cast<uint64_t>(n_ids) ? pos[cur[i]] : 0;
 }
 
 __global__ void iota_kernel(int32_t* __restrict__ v, int64_t n) {
@@ -130,7 +133,7 @@ extern "C" int ps_plan_layer(const int32_t* nb, int64_t n, int T, const int64_t*
     PS_CUDA_CHECK(cudaMemsetAsync(flag, 0, static_cast<size_t>(n_ids + 1) * sizeof(int32_t), stream));
     const int64_t n_nb = n * T;
     if (n > 0) {
-        mark_kernel<<<blocks_for(n_nb), 256, 0, stream>>>(nb, n_nb, cur, n, with_self, flag);
+        mark_kernel<<<blocks_for(n_nb), 256, 0, stream>>>(nb, n_nb, cur, n, with_self, n_ids, flag);
         PS_LAUNCH_CHECK();
     }
     size_t tmp_bytes = 0;
@@ -142,7 +145,7 @@ extern "C" int ps_plan_layer(const int32_t* nb, int64_t n, int T, const int64_t*
     compact_kernel<<<blocks_for(n_ids), 256, 0, stream>>>(flag, pos, n_ids, uniq_i64, uniq_i32);
     PS_LAUNCH_CHECK();
     if (n > 0) {
-        inverse_kernel<<<blocks_for(n_nb), 256, 0, stream>>>(pos, nb, n_nb, cur, n, with_self, nbz, self_rows);
+        inverse_kernel<<<blocks_for(n_nb), 256, 0, stream>>>(pos, nb, n_nb, cur, n, with_self, n_ids, nbz, self_rows);
         PS_LAUNCH_CHECK();
     }
     PS_CUDA_CHECK(cudaMemcpyAsync(count_out, pos + n_ids, sizeof(int32_t), cudaMemcpyDeviceToDevice, stream));

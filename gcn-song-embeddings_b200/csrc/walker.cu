@@ -27,6 +27,7 @@ struct ps_graph {
     const int32_t* indices;
     int64_t n_tracks, n_cols, n_entries;
     uint32_t* indptr32;  // owned compact copy of indptr (n_entries < 2^32), halves the bytes per hop
+    bool use32;          // ps_graph_use_indptr32
 };
 
 namespace {
@@ -408,7 +409,7 @@ extern "C" int ps_graph_create(const int64_t* indptr, const int32_t* indices, in
     PS_CUDA_CHECK(cudaFreeAsync(bad, stream));
     if (h_bad != 0)
         return ps_fail(PS_ERR_GRAPH, "%llu node(s) have no successors or a malformed indptr; the reference's walker raises on them (pinsage_model.py:42)", h_bad);
-    ps_graph* g = new ps_graph{indptr, indices, n_tracks, n_cols, n_entries, nullptr};
+    ps_graph* g = new ps_graph{indptr, indices, n_tracks, n_cols, n_entries, nullptr, true};
     if (n_entries < (1ll << 32)) {  // 4-byte row offsets for the walker
         if (cudaMalloc(&g->indptr32, static_cast<size_t>(n_nodes + 1) * sizeof(uint32_t)) != cudaSuccess) {
             g->indptr32 = nullptr;
@@ -423,6 +424,13 @@ extern "C" int ps_graph_create(const int64_t* indptr, const int32_t* indices, in
     return PS_OK;
 }
 
+extern "C" int ps_graph_use_indptr32(ps_graph_t* g, int on) {
+    PS_REQUIRE(g != nullptr, "null pointer");
+    const int old = g->use32 ? 1 : 0;
+    g->use32 = on != 0;
+    return old;
+}
+
 extern "C" int ps_graph_destroy(ps_graph_t* g) {
     if (g != nullptr && g->indptr32 != nullptr) cudaFree(g->indptr32);
     delete g;
@@ -434,7 +442,7 @@ extern "C" int ps_walk_topt(const ps_graph_t* g, const int64_t* sources, int64_t
                             int32_t* out_nodes_i32, float* out_w_f32, int32_t* out_trace, ps_stream_t stream) {
     PS_REQUIRE(g != nullptr && (sources != nullptr || n == 0), "null pointer");
     PS_REQUIRE(fixed_len >= 0, "fixed_len must be >= 0");
-    if (g->indptr32 != nullptr)
+    if (g->indptr32 != nullptr && g->use32)
         return launch_walk<uint32_t, false>(g->indptr32, g->indices, sources, nullptr, n, n_hops, alpha, fixed_len, T, seed,
                                             out_nodes_i64, out_w_f64, out_nodes_i32, out_w_f32, out_trace,
                                             static_cast<cudaStream_t>(stream));

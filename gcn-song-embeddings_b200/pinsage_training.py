@@ -104,10 +104,14 @@ def sample_hard_negatives(all_ids, pos_batch, nbhds, min_rank, max_rank, referen
     the neighbourhood table instead of the queries' rows (:84); reference_compat=True
     reproduces that, False uses the queries' rows."""
     queries = pos_batch[:, 0]
-    nb_nodes = nbhds[1]
     rnd_ranks = torch.randint(min_rank, max_rank, (queries.shape[0],), device=pos_batch.device)
     rows = torch.arange(queries.shape[0], device=pos_batch.device) if reference_compat else queries
-    hard_neg = nb_nodes.to(pos_batch.device)[rows, rnd_ranks].to(torch.int64)
+    if pos_batch.is_cuda:
+        # the engine's device-resident int32 table (uploaded once), not the host int64 [N, 100] tuple: only B ids move
+        from ps_engine import NeighborTable
+        hard_neg = NeighborTable.of(nbhds).nodes[rows, rnd_ranks].to(torch.int64)
+    else:
+        hard_neg = nbhds[1][rows.cpu(), rnd_ranks.cpu()].to(torch.int64)
     batch = torch.cat((pos_batch, hard_neg.unsqueeze(1)), dim=1)
     nodeset = batch.flatten().unique().to(torch.int64)
     return batch, nodeset
@@ -115,6 +119,7 @@ def sample_hard_negatives(all_ids, pos_batch, nbhds, min_rank, max_rank, referen
 
 _sampler_state = {"seed": None, "step": 0}
 _sampler_lock = threading.Lock()
+SAMPLER_RANK = 0  # data-parallel rank mixed into the device sampler's Philox counter (set by ps_dist.attach)
 
 
 def sample_batch_device(all_ids, positives, batch_size):
@@ -132,7 +137,9 @@ def sample_batch_device(all_ids, positives, batch_size):
         if st["seed"] != torch.initial_seed():
             st["seed"], st["step"] = torch.initial_seed(), 0
         st["step"] += 1
-        seed, step = st["seed"], st["step"]
+        # the rank occupies the high bits of the counter word: replicas that were seeded identically
+        # (torch.manual_seed(S) on every rank) still draw different batches
+        seed, step = st["seed"], st["step"] | (int(SAMPLER_RANK) << 40)
     return ps_native.sample_batch(positives, all_ids, all_ids.shape[0], batch_size, seed, step)
 
 
@@ -376,6 +383,9 @@ class PinSage():
 
     def load_model(self):
         load_path = os.path.join(BASE_RUN_DIR, self.run_name, "state.pt")
+        if self.world_size > 1:  # data parallel: nobody reads while rank 0 may still be replacing the file
+            import ps_dist
+            ps_dist.barrier()
         if os.path.isfile(load_path):
             prog = torch.load(load_path, map_location="cuda")
             self.e = prog["epochs_done"]
@@ -385,9 +395,17 @@ class PinSage():
             print(f"Loaded existing model from {load_path}.")
 
     def save_model(self):
+        """state.pt in the reference's format (pinsage_training.py:288-295).  Data parallel: the replicas are
+        identical, so only rank 0 writes; the file is written beside its destination and renamed over it, so a reader
+        (or a crash) never sees a torn checkpoint."""
+        if self.world_size > 1 and self.rank != 0:
+            return
         prog = {"epochs_done": self.e, "batches_done": self.b,
                 "model_state": self.model.state_dict(), "optimizer_state": self.optimizer.state_dict()}
-        torch.save(prog, os.path.join(BASE_RUN_DIR, self.run_name, "state.pt"))
+        path = os.path.join(BASE_RUN_DIR, self.run_name, "state.pt")
+        tmp = f"{path}.tmp{os.getpid()}"
+        torch.save(prog, tmp)
+        os.replace(tmp, path)
 
 
 def save_embeddings(trainer, dataset, base_run_dir=BASE_RUN_DIR, override_run_name=None):

@@ -79,10 +79,24 @@ def broadcast_parameters(model, src=0):
             dist.broadcast(p.data, src=src)
 
 
+def seed_rank_streams(rank: int, world_size: int):
+    """Make the batch samplers of the replicas draw DIFFERENT batches even when every rank called the same
+    torch.manual_seed(S): the rank is mixed into the device sampler's Philox counter (pinsage_training.SAMPLER_RANK)
+    and the torch generators behind the randperm / randint fallback paths are re-seeded with a per-rank offset.
+    Without this an identically seeded N-GPU run computes N copies of one gradient."""
+    import pinsage_training as pst
+    pst.SAMPLER_RANK = int(rank)
+    if world_size > 1 and rank > 0:
+        seed = (torch.initial_seed() + 0x9E3779B97F4A7C15 * rank) & 0x7FFFFFFFFFFFFFFF
+        torch.manual_seed(seed)  # seeds the CPU and every CUDA generator
+
+
 def attach(trainer, rank: int, world_size: int):
     """Turn a PinSage trainer into one data-parallel replica: parameters broadcast from
-    rank 0, gradient mean-allreduce before every optimiser step."""
+    rank 0, gradient mean-allreduce before every optimiser step, rank-distinct batch streams.
+    Checkpoints: only rank 0 writes state.pt (PinSage.save_model), every rank loads it after a barrier."""
     trainer.rank, trainer.world_size = rank, world_size
+    seed_rank_streams(rank, world_size)
     if world_size > 1:
         broadcast_parameters(trainer.model)
         engine = trainer.model.engine

@@ -54,6 +54,22 @@ class NeighborTable:
         self.w = _dev(weights, None, device).to(torch.float32).contiguous()
         self.n, self.Tp = self.nodes.shape
         self.scratch = {}
+        self._sanitize()
+
+    def _sanitize(self):
+        """One-time range check of the neighbour ids (the plan builder indexes dense [N] maps with them).  A
+        neighborhoods.pt written by the reference can hold zero-weight FILLER ids >= n_items: its topk runs over the
+        dense [n, N+C] row (pinsage_model.py:93-107).  Those slots are remapped to the
+        row's own id (weight 0: they contribute nothing and add no frontier node); an out-of-range id with a
+        non-zero weight raises IndexError, as indexing the reference's feature table with it would."""
+        if self.nodes.numel() == 0:
+            return
+        bad = (self.nodes < 0) | (self.nodes >= self.n)
+        if bool(bad.any()):
+            if bool((bad & (self.w != 0)).any()):
+                raise IndexError("neighbourhood table holds node ids outside [0, n_items) with non-zero weight")
+            own = torch.arange(self.n, dtype=torch.int32, device=self.nodes.device)[:, None].expand_as(self.nodes)
+            self.nodes = torch.where(bad, own, self.nodes).contiguous()
 
     def lookup(self, cur: torch.Tensor, T: int):
         """(neighbours int32 [n, T], weights float32 [n, T]) of the nodes `cur` (int64 on the device)."""
@@ -118,6 +134,7 @@ class LayerPlan:
     pair_q: Optional[torch.Tensor] = None   # int32 [n*T]   (backward)
     chunk_off: Optional[torch.Tensor] = None  # int32 [nz+1] first work chunk of every z-row (backward)
     chunk_row: Optional[torch.Tensor] = None  # int32 [max_chunks] z-row of every work chunk (backward)
+    nodes: Optional[torch.Tensor] = None      # int64 [n] node id of every target (sorted, distinct)
 
 
 @dataclass
@@ -172,7 +189,7 @@ def build_plan(top: torch.Tensor, n_layers: int, T: int, table: NeighborTable, n
                 nxt, zrows = uniq, None
             else:
                 nxt, zrows, self_rows = None, uniq, cur.to(torch.int32)
-            lp = LayerPlan(n=n, nz=nz, self_rows=self_rows, nbz=nbz, w=w, zrows=zrows)
+            lp = LayerPlan(n=n, nz=nz, self_rows=self_rows, nbz=nbz, w=w, zrows=zrows, nodes=cur)
             if need_backward:
                 lp.pair_q, lp.seg_off, lp.chunk_off, lp.chunk_row = nat.plan_transpose(nbz, nz)
             plan.layers[l] = lp
@@ -189,7 +206,7 @@ def build_plan(top: torch.Tensor, n_layers: int, T: int, table: NeighborTable, n
             nbz = inv.view(n, T).to(torch.int32).contiguous()
             self_rows = cur.to(torch.int32).contiguous()
             zrows, nz, nxt = zr.to(torch.int32).contiguous(), zr.numel(), None
-        lp = LayerPlan(n=n, nz=nz, self_rows=self_rows, nbz=nbz, w=w, zrows=zrows)
+        lp = LayerPlan(n=n, nz=nz, self_rows=self_rows, nbz=nbz, w=w, zrows=zrows, nodes=cur)
         if need_backward:
             flat = nbz.reshape(-1)
             skeys, order = torch.sort(flat, stable=True)  # q ascends inside a segment: reproducible backward sums
@@ -215,7 +232,7 @@ class Prepared:
     def tensors(self):
         out = [self.batch, self.triples, self.counts, self.plan.top]
         for lp in self.plan.layers:
-            out += [t for t in (lp.self_rows, lp.nbz, lp.w, lp.zrows, lp.seg_off, lp.pair_q, lp.chunk_off, lp.chunk_row) if t is not None]
+            out += [t for t in (lp.self_rows, lp.nbz, lp.w, lp.zrows, lp.seg_off, lp.pair_q, lp.chunk_off, lp.chunk_row, lp.nodes) if t is not None]
         return out
 
 

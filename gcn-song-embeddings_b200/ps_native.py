@@ -41,6 +41,7 @@ _SIGNATURES = {
     "ps_gemm_tc_reserve_sms": ([c_int], c_int),
     "ps_graph_create": ([c_void_p, c_void_p, c_int64, c_int64, c_int64, ctypes.POINTER(c_void_p), c_void_p], c_int),
     "ps_graph_destroy": ([c_void_p], c_int),
+    "ps_graph_use_indptr32": ([c_void_p, c_int], c_int),
     "ps_walk_topt": ([c_void_p, c_void_p, c_int64, c_int, c_double, c_int, c_int, c_uint64,
                       c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p], c_int),
     "ps_trace_topt": ([c_void_p, c_void_p, c_int64, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p], c_int),
@@ -194,6 +195,10 @@ class GraphHandle:
         check(lib().ps_graph_create(_p(self.indptr), _p(self.indices), self.n_tracks, self.n_cols,
                                     self.indices.numel(), ctypes.byref(handle), _stream()))
         self._h = handle
+
+    def use_indptr32(self, on: bool) -> bool:
+        """False forces the walker's 8-byte row-offset path (what graphs with >= 2^32 CSR entries take)."""
+        return bool(lib().ps_graph_use_indptr32(self._h, int(bool(on))))
 
     def __del__(self):
         h, self._h = getattr(self, "_h", None), None

@@ -46,6 +46,10 @@ int ps_set_device(int device);
 int ps_graph_create(const int64_t* indptr, const int32_t* indices, int64_t n_tracks, int64_t n_cols,
                     int64_t n_entries, ps_graph_t** out, ps_stream_t stream);
 int ps_graph_destroy(ps_graph_t* g);
+/* The walker reads 4-byte row offsets (a compact copy owned by the handle) when the CSR has < 2^32 entries and the
+ * caller's 8-byte indptr otherwise (BASELINE.json configs[3]: 2 x 10^9 entries).  on = 0 forces the 8-byte path on a
+ * small graph (parity tests of that path), on = 1 restores the default.  Returns the previous setting (or < 0). */
+int ps_graph_use_indptr32(ps_graph_t* g, int on);
 
 /* ---- K1+K2: restart random walks fused with the visit-count top-T reduction.
  *      Replaces do_random_walks + sample_neighborhood + sample_neighborhood_topt

@@ -227,19 +227,44 @@ def make_params(n_layers, dims, rng: np.random.RandomState, dtype=torch.float32)
     return p
 
 
-def conv_layer_forward(h, nodeset, nb_nodes, nb_weights, Qw, Qb, Ww, Wb):
+def _leaky_with_signs(pre, row_nodes, forced):
+    """leaky_relu(pre) where, for the few entries listed in `forced` = [(node id, column, positive?)], the branch
+    of the activation is GIVEN instead of decided by the sign of `pre`.  leaky_relu's derivative jumps by 100x at
+    0, so an entry whose pre-activation lies within fp32 rounding of 0 gets its branch from the summation order of
+    whoever computes it (MKL, a CUDA-core loop, the tensor core) -- no two fp32 implementations agree on those.
+    The parity tests pass the product's decisions for exactly the entries a float64 evaluation proves to be
+    rounding-ambiguous, so that both sides differentiate the same function.  Values change by < 1e-6 absolute.
+    `pre` is [rows, D]; `row_nodes` [rows] the node id each row belongs to."""
+    act = torch.nn.functional.leaky_relu(pre, LEAKY_SLOPE)
+    if not forced:
+        return act
+    rr, cc, slope = [], [], []
+    for node, col, positive in forced:
+        hit = (row_nodes == int(node)).nonzero().flatten()
+        rr.append(hit); cc.append(torch.full_like(hit, int(col)))
+        slope.append(torch.full((hit.numel(),), 1.0 if positive else LEAKY_SLOPE, dtype=pre.dtype))
+    rr, cc, slope = torch.cat(rr), torch.cat(cc), torch.cat(slope)
+    if rr.numel() == 0:
+        return act
+    return act.index_put((rr, cc), pre[rr, cc] * slope)
+
+
+def conv_layer_forward(h, nodeset, nb_nodes, nb_weights, Qw, Qb, Ww, Wb, forced=None):
     """One PinSage convolution; restates `ConvLayer.forward` (pinsage_model.py:189-212).
     leaky_relu(Q .) on the T gathered neighbour rows, importance-weighted mean in float64
     (the weights are f64, :202), concat with the self row, `.float()`, leaky_relu(W .),
-    row L2-normalise without eps (:210)."""
+    row L2-normalise without eps (:210).  `forced` = {"Q": [...], "W": [...]} (optional, tests only): activation
+    branches given for rounding-ambiguous entries, see _leaky_with_signs."""
     din = Qw.shape[1]
     n, T = nb_nodes.shape
+    forced = forced or {}
     self_h = h[nodeset, :din]
-    nb_h = h[nb_nodes.reshape(-1), :din].reshape(n, T, din)
-    nb_h = torch.nn.functional.leaky_relu(torch.nn.functional.linear(nb_h, Qw, Qb), LEAKY_SLOPE)
+    nb_flat = nb_nodes.reshape(-1)
+    pre = torch.nn.functional.linear(h[nb_flat, :din], Qw, Qb)
+    nb_h = _leaky_with_signs(pre, nb_flat, forced.get("Q")).reshape(n, T, -1)
     agg = (nb_weights[:, :, None] * nb_h).sum(1) / nb_weights.sum(1, keepdim=True)
     cat = torch.cat([self_h, agg], 1).float()
-    new_h = torch.nn.functional.leaky_relu(torch.nn.functional.linear(cat, Ww, Wb), LEAKY_SLOPE)
+    new_h = _leaky_with_signs(torch.nn.functional.linear(cat, Ww, Wb), nodeset, forced.get("W"))
     return new_h / new_h.norm(dim=1, keepdim=True)
 
 
@@ -252,7 +277,7 @@ def _put(h, nodeset, x):
     return new_h
 
 
-def model_forward(params, features, nodeset, nbhds, T, n_layers):
+def model_forward(params, features, nodeset, nbhds, T, n_layers, forced=None):
     """`PinSageModel.forward` (pinsage_model.py:246-265) including the full-table
     put/get round trips, so that autograd reproduces the duplicate-node gradient factor
     of the final put/get pair (:260,265)."""
@@ -265,7 +290,8 @@ def model_forward(params, features, nodeset, nbhds, T, n_layers):
         ns_t = torch.from_numpy(ns)
         new = conv_layer_forward(h, ns_t, torch.from_numpy(nb), torch.from_numpy(w),
                                  params[f"conv_layers.{l}.Q.weight"], params[f"conv_layers.{l}.Q.bias"],
-                                 params[f"conv_layers.{l}.W.weight"], params[f"conv_layers.{l}.W.bias"])
+                                 params[f"conv_layers.{l}.W.weight"], params[f"conv_layers.{l}.W.bias"],
+                                 forced=(forced or {}).get(l))
         h = _put(h, ns_t, new)
     new = torch.nn.functional.linear(
         torch.nn.functional.leaky_relu(torch.nn.functional.linear(new, params["G1.weight"], params["G1.bias"]), LEAKY_SLOPE),
@@ -284,15 +310,16 @@ def max_margin_loss(h_q, h_pos, h_neg, margin):
     return torch.stack([d, torch.zeros_like(d)], 1).max(1).values.mean()
 
 
-def train_batch_grads(params, features, batch, nbhds, T, n_layers, margin):
+def train_batch_grads(params, features, batch, nbhds, T, n_layers, margin, forced=None):
     """Loss and parameter gradients of one (q, pos, neg) batch; restates the first half
     of `PinSage.train_batch` (pinsage_training.py:184-190): three separate forwards, the
-    max-margin loss, backward."""
+    max-margin loss, backward.  `forced` = {layer: {"Q": [(node, col, positive?)], "W": [...]}}: see
+    _leaky_with_signs (tests at sizes where rounding-ambiguous activations exist)."""
     p = {k: v.clone().detach().requires_grad_(True) for k, v in params.items()}
     batch = torch.as_tensor(batch, dtype=torch.int64)
-    hq = model_forward(p, features, batch[:, 0], nbhds, T, n_layers)
-    hp = model_forward(p, features, batch[:, 1], nbhds, T, n_layers)
-    hn = model_forward(p, features, batch[:, 2], nbhds, T, n_layers)
+    hq = model_forward(p, features, batch[:, 0], nbhds, T, n_layers, forced)
+    hp = model_forward(p, features, batch[:, 1], nbhds, T, n_layers, forced)
+    hn = model_forward(p, features, batch[:, 2], nbhds, T, n_layers, forced)
     loss = max_margin_loss(hq, hp, hn, margin)
     loss.backward()
     return loss.detach(), {k: v.grad.detach() for k, v in p.items()}, (hq.detach(), hp.detach(), hn.detach())
@@ -308,11 +335,11 @@ class OracleTrainer:
         self.features, self.nbhds, self.T, self.n_layers, self.margin = features, nbhds, T, n_layers, margin
         self.optimizer = torch.optim.Adam(list(self.params.values()), lr=lr)
 
-    def train_batch(self, batch):
+    def train_batch(self, batch, forced=None):
         batch = torch.as_tensor(batch, dtype=torch.int64)
-        hq = model_forward(self.params, self.features, batch[:, 0], self.nbhds, self.T, self.n_layers)
-        hp = model_forward(self.params, self.features, batch[:, 1], self.nbhds, self.T, self.n_layers)
-        hn = model_forward(self.params, self.features, batch[:, 2], self.nbhds, self.T, self.n_layers)
+        hq = model_forward(self.params, self.features, batch[:, 0], self.nbhds, self.T, self.n_layers, forced)
+        hp = model_forward(self.params, self.features, batch[:, 1], self.nbhds, self.T, self.n_layers, forced)
+        hn = model_forward(self.params, self.features, batch[:, 2], self.nbhds, self.T, self.n_layers, forced)
         loss = max_margin_loss(hq, hp, hn, self.margin)
         self.optimizer.zero_grad()
         loss.backward()

@@ -61,6 +61,17 @@ def _worker(rank, world, port, out):
         table[lo:hi] = want[lo:hi]
         ps_dist.all_gather_rows_(table, lo, hi, world)
         assert torch.equal(table, want), n
+    # identically seeded replicas still draw DIFFERENT batches once attached (ps_dist.seed_rank_streams)
+    import pinsage_training as pst
+    torch.manual_seed(1234)                      # the mistake a data-parallel script makes on every rank
+    ps_dist.seed_rank_streams(rank, world)
+    assert pst.SAMPLER_RANK == rank
+    positives = torch.arange(4000).view(2000, 2)
+    b, _ = pst.sample_batch(torch.arange(5000), positives, 64, None, hard_negatives=False)
+    both = [torch.zeros_like(b) for _ in range(world)]
+    dist.all_gather(both, b)
+    assert not torch.equal(both[0], both[1])
+    assert not torch.equal(both[0][:, 2], both[1][:, 2])
     ps_dist.barrier()
     out.put(rank)
     dist.destroy_process_group()

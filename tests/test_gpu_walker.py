@@ -99,6 +99,39 @@ def test_walker_properties_large(nat):
     assert not torch.equal(other["nodes"], nb)
 
 
+@pytest.mark.parametrize("wide_indptr", [False, True])
+def test_walker_bit_exact_on_large_graph(nat, wide_indptr):
+    """Traces and top-T of 384 sources of a 200 k-track / 4 M-edge graph (skewed degrees, hub playlists of 5000
+    tracks) equal the oracle's bit for bit -- on the 4-byte row-offset path and on the 8-byte one that graphs with
+    >= 2^32 CSR entries take (BASELINE.json configs[3]), forced here through ps_graph_use_indptr32."""
+    import ps_synth
+    n_tracks, n_cols = 200_000, 40_000
+    g = ps_synth.make_graph(n_tracks, n_cols, 4_000_000, seed=5, device="cuda")
+    gh = g.device()
+    indptr, indices = g.indptr.numpy(), g.indices.numpy()
+    deg = np.diff(indptr[: n_tracks + 1])
+    src = np.unique(np.concatenate([np.argsort(-deg)[:64], np.argsort(deg)[:64], np.random.RandomState(1).randint(0, n_tracks, 256)]))
+    old = gh.use_indptr32(not wide_indptr)
+    try:
+        for n_hops, alpha, fixed_len, T in ((500, 0.85, 0, 100), (300, 0.85, 3, 50)):
+            out = nat.walk_topt(gh, torch.from_numpy(src), n_hops, alpha, T, seed=0xBADC0DE5, fixed_len=fixed_len, want_i32=True, want_trace=True)
+            want = oracle.do_random_walks_philox(indptr, indices, src, n_hops, alpha, 0xBADC0DE5, fixed_len)
+            assert np.array_equal(out["trace"].cpu().numpy().astype(np.int64), want)
+            ow, onb = oracle.topt_from_trace(want, src, T)
+            assert np.array_equal(out["weights"].cpu().numpy().view(np.int64), ow.view(np.int64))
+            assert np.array_equal(out["nodes"].cpu().numpy(), onb)
+            assert np.array_equal(out["nodes_i32"].cpu().numpy().astype(np.int64), onb)
+    finally:
+        gh.use_indptr32(old)
+    # both paths give the same table over ALL sources (size-independent: path A == path B)
+    all_src = torch.arange(0, n_tracks, device="cuda")
+    a = nat.walk_topt(gh, all_src, 500, 0.85, 100, seed=3, want_i64=False, want_i32=True)
+    gh.use_indptr32(False)
+    b = nat.walk_topt(gh, all_src, 500, 0.85, 100, seed=3, want_i64=False, want_i32=True)
+    gh.use_indptr32(True)
+    assert torch.equal(a["nodes_i32"], b["nodes_i32"]) and torch.equal(a["weights_f32"], b["weights_f32"])
+
+
 def test_graph_with_dead_end_is_rejected(nat):
     indptr = torch.tensor([0, 1, 1, 2])  # track 1 has no successors
     indices = torch.tensor([2, 0], dtype=torch.int32)

@@ -183,3 +183,17 @@ def test_sample_batch_philox_properties():
     assert np.array_equal(a, b) and not np.array_equal(a, c)
     oracle.check_batch_properties(a, positives, 3000)
     assert a.shape == (128, 3)
+
+
+def test_forced_activation_branches():
+    """oracle._leaky_with_signs (the hook of the rounding-ambiguity rule, tests/parity_util.py): listed entries take
+    the GIVEN leaky_relu branch in value and derivative, everything else is plain leaky_relu."""
+    import torch
+    pre = torch.tensor([[1e-8, -2.0], [-1e-8, 3.0], [1e-8, 1.0]], requires_grad=True)
+    nodes = torch.tensor([7, 9, 7])
+    out = oracle._leaky_with_signs(pre, nodes, [(7, 0, False), (9, 0, True)])
+    out.sum().backward()
+    assert torch.allclose(pre.grad, torch.tensor([[0.01, 0.01], [1.0, 1.0], [0.01, 1.0]]))
+    assert torch.allclose(out.detach(), torch.tensor([[1e-10, -0.02], [-1e-8, 3.0], [1e-10, 1.0]]))
+    plain = oracle._leaky_with_signs(pre.detach(), nodes, None)
+    assert torch.equal(plain, torch.nn.functional.leaky_relu(pre.detach(), 0.01))
