@@ -56,7 +56,7 @@ UNIT = "nodes/s"
 WORKLOADS = {
     # BASELINE.json configs[2]
     "cfg3": dict(n_tracks=1_000_000, n_cols=200_000, n_edges=40_000_000, din=256, n_layers=2, T=50, batch=1024,
-                 n_pos=10_000_000, ref_batch=8),
+                 n_pos=10_000_000, ref_batch=128),
     # BASELINE.json configs[0] stand-in (dataset_micro is not in the reference checkout): its size, the reference's defaults
     "cfg1": dict(n_tracks=4_324, n_cols=1_500, n_edges=60_000, din=512, n_layers=2, T=3, batch=128, n_pos=5_000, ref_batch=128),
     # BASELINE.json configs[1] stand-in at dataset_final_intersect scale
@@ -164,9 +164,13 @@ def roofline_from_profile(summary, steps, peaks):
         peak, unit, bound = peaks["tflops"], "TFLOP/s", "tensor"
         # fp32 parity needs the 3xTF32 split: every algorithmic FLOP is 3 tf32 tensor-core FLOPs, and dense tf32 runs at
         # half the bf16 rate, so the fp32-equivalent ceiling of the tensor pipe is peak / 6
-        extra = {"note": "fp32-in/fp32-out GEMM computed as an error-compensated 3xTF32 product on tcgen05",
+        extra = {"note": "fp32-in/fp32-out GEMM computed as an error-compensated 3xTF32 product on tcgen05: `frac` divides the "
+                         "algorithmic fp32 FLOPs by the bf16 peak; the tensor pipe executes 3 tf32 MMAs per algorithmic product",
                  "issued_tf32_tflops": round(3 * achieved, 2), "fp32_equivalent_ceiling": round(peak / 6, 1),
                  "frac_of_fp32_equivalent_ceiling": round(achieved / (peak / 6), 4)}
+        if peaks.get("tf32_tflops_sustained"):  # measured in this run (cuBLAS TF32 GEMM): the pipe's own dense rate
+            extra["tf32_dense_measured_tflops"] = peaks["tf32_tflops_sustained"]
+            extra["tensor_pipe_frac_vs_measured_tf32"] = round(3 * achieved / peaks["tf32_tflops_sustained"], 4)
     else:
         achieved = top["bytes"] / top["launches"] / (per_launch_ms * 1e-3) / 1e9
         peak, unit, bound = peaks["hbm_gbs"], "GB/s", "hbm"
@@ -186,7 +190,9 @@ def roofline_from_profile(summary, steps, peaks):
 # CPU baseline (oracle port of the reference's train step)
 # ------------------------------------------------------------------------------------------
 
-def cpu_train_baseline(features_cpu, nbhds_cpu, dims, n_layers, T, batches, warmup, margin=1e-5):
+def cpu_train_baseline(features_cpu, nbhds_cpu, dims, n_layers, T, batches, warmup, margin=1e-5, budget_s=150.0):
+    """Oracle port of the reference's train step on the host cores.  Stops early once `budget_s` seconds of timed
+    steps have run (the arm must finish within minutes); returns (nodes/s, s/step, steps timed)."""
     from oracle import oracle
     params = oracle.make_params(n_layers, dims, np.random.RandomState(0))
     tr = oracle.OracleTrainer(params, features_cpu, nbhds_cpu, T=T, n_layers=n_layers, margin=margin)
@@ -197,8 +203,49 @@ def cpu_train_baseline(features_cpu, nbhds_cpu, dims, n_layers, T, batches, warm
         dt = time.perf_counter() - t0
         if i >= warmup:
             times.append(dt)
+            if sum(times) > budget_s:
+                break
     B = batches[0].shape[0]
-    return 3 * B / (sum(times) / len(times)), sum(times) / len(times)
+    return 3 * B / (sum(times) / len(times)), sum(times) / len(times), len(times)
+
+
+def cpu_walk_baseline(indptr, indices, n_tracks, n_hops=500, alpha=0.85, T=100, per_core=8192):
+    """The oracle's restatement of do_random_walks + sample_neighborhood_topt (pinsage_model.py:32-53, 88-107;
+    numpy, vectorised over sources, steps sequential) on the box's host cores: one core on `per_core` sources, then
+    every core at once on its own disjoint source range (one process per core, oracle/walk_baseline.py, started
+    together through a file barrier).  NOTE the restatement is ~500x faster per core than the reference's own
+    pure-Python loop (1.85e4 steps/s/core): it is the stronger baseline."""
+    import shutil
+    cores = len(os.sched_getaffinity(0))
+    per_core = max(64, min(per_core, n_tracks // max(cores, 1)))
+    tmp = tempfile.mkdtemp(prefix="pswalk_", dir="/dev/shm" if os.path.isdir("/dev/shm") else None)
+    path = os.path.join(tmp, "graph.npy")
+    script = os.path.join(ROOT, "oracle", "walk_baseline.py")
+    env = dict(os.environ, OMP_NUM_THREADS="1", CUDA_VISIBLE_DEVICES="")
+
+    def run(n_proc):
+        sync = tempfile.mkdtemp(prefix="sync_", dir=tmp)
+        procs = [subprocess.Popen([sys.executable, script, path, str(c * per_core), str((c + 1) * per_core), str(n_hops), str(alpha), str(T), sync],
+                                  stdout=subprocess.PIPE, text=True, env=env) for c in range(n_proc)]
+        t0 = time.time()
+        while len([f for f in os.listdir(sync) if f.startswith("ready.")]) < n_proc and time.time() - t0 < 240:
+            if any(p.poll() is not None for p in procs):
+                break
+            time.sleep(0.01)
+        open(os.path.join(sync, "go"), "w").close()
+        outs = [p.communicate(timeout=600)[0] for p in procs]
+        return max(float(o.strip().splitlines()[-1]) for o in outs)
+
+    try:
+        np.save(path, np.concatenate([np.array([indptr.shape[0] - 1], dtype=np.int64), indptr.astype(np.int64), indices.astype(np.int64)]))
+        single = run(1)
+        allc = run(cores)
+    finally:
+        shutil.rmtree(tmp, ignore_errors=True)
+    return {"single_core_steps_per_s": round(per_core * n_hops / single, 1), "all_cores_steps_per_s": round(cores * per_core * n_hops / allc, 1),
+            "cores": cores, "kind": "port",
+            "sample": f"{per_core} sources x {n_hops} hops + top-{T} per core (oracle.do_random_walks_philox + topt_from_trace, numpy); "
+                      f"the reference's own Python loop does 1.85e4 steps/s/core (BASELINE.md section 2)"}
 
 
 def needed_nbhds_cpu(indptr, indices, n_tracks, batches, T, n_layers, n_hops=500, alpha=0.85, Tp=100, seed=7):
@@ -244,16 +291,18 @@ def run_reference(args, wl):
         batches.append(np.concatenate([pairs, neg], 1).astype(np.int64))
     nbhds = needed_nbhds_cpu(indptr.numpy(), indices.numpy(), wl["n_tracks"], batches, wl["T"], wl["n_layers"])
     setup_s = time.perf_counter() - t_setup
-    value, s_per_step = cpu_train_baseline(feats, nbhds, (wl["din"], 512, 128), wl["n_layers"], wl["T"], batches, args.warmup)
+    value, s_per_step, timed = cpu_train_baseline(feats, nbhds, (wl["din"], 512, 128), wl["n_layers"], wl["T"], batches, args.warmup)
     cores = torch.get_num_threads()
     line = {"impl": "reference", "metric": METRIC, "value": round(value, 3), "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(s_per_step * 1e3, 2),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": workload_config(args.workload, wl, 1),
+            "config": workload_config(args.workload, wl, 1, batch=B, parallelism=f"cpu{cores}"),
             "cpu_baseline": {"value": round(value, 3), "unit": UNIT, "cores": cores, "kind": "port",
-                             "sample": f"{args.steps} steps of {B} triples (3*{B} nodes) on the full {wl['n_tracks']}-track graph, T={wl['T']}"},
+                             "sample": f"{timed} timed steps of {B} triples (3*{B} nodes) on the full {wl['n_tracks']}-track graph, T={wl['T']}"
+                                       + ("" if B == wl["batch"] else f" -- a bounded sample: the GPU arm's batch is {wl['batch']}; a CPU step at that batch "
+                                          "needs tens of GB of dense autograd state and (at cfg3) minutes per step")},
             "e2e": {"value": round(value, 3), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-            "setup_s": round(setup_s, 1)}
+            "steps_timed": timed, "setup_s": round(setup_s, 1)}
     print(json.dumps(line), flush=True)
     return 0
 
@@ -261,11 +310,14 @@ def run_reference(args, wl):
 SAMPLING_DESC = ["precomputed neighbourhoods (n_hops=500, alpha=0.85, T_precomp=100), easy negatives"]
 
 
-def workload_config(name, wl, n_gpus):
+def workload_config(name, wl, n_gpus, batch=None, parallelism=None):
+    """`batch` = triples per step and GPU that the arm REALLY runs (the reference arm's bounded sample uses
+    wl['ref_batch'], not wl['batch']: its line says so here, so the two arms only compare as same-config when they are)."""
+    batch = wl["batch"] if batch is None else batch
     return {"workload": f"{name}: synthetic bipartite {wl['n_tracks']} tracks / {wl['n_cols']} playlists / {wl['n_edges']} edges, "
-                        f"{wl['din']}-d features, {wl['n_layers']} layers, T={wl['T']}, hidden 512, out 128, batch {wl['batch']}/GPU",
+                        f"{wl['din']}-d features, {wl['n_layers']} layers, T={wl['T']}, hidden 512, out 128, batch {batch}/GPU",
             "sampling": SAMPLING_DESC[0],
-            "global_batch": wl["batch"] * n_gpus, "parallelism": f"dp{n_gpus}",
+            "global_batch": batch * n_gpus, "parallelism": parallelism or f"dp{n_gpus}",
             "l2_policy": ("inputs larger than L2 (features 1.0 GB, transformed rows up to 2 GB per step vs 126 MB L2)" if name == "cfg3"
                           else "working set smaller than L2 at this size: a 256 MB buffer is written between steps" if wl["n_tracks"] * wl["din"] * 4 < 120e6
                           else "features larger than L2")}
@@ -274,6 +326,98 @@ def workload_config(name, wl, n_gpus):
 # ------------------------------------------------------------------------------------------
 # our arm
 # ------------------------------------------------------------------------------------------
+
+def _drain(pending):
+    for f in pending:
+        if not f.cancel():
+            try:
+                f.result()
+            except Exception:
+                pass
+    pending.clear()
+
+
+def train_leg(trainer, steps, warmup, world, clock_dev=None, flush=None):
+    """K timed steps of trainer.train_batch through the same prefetch pipeline as the headline leg (device-drawn
+    batches), CUDA events + barrier on both sides, max over ranks.  Used for the `extra` sub-lines."""
+    import ps_dist
+    from collections import deque
+    pend = deque([trainer.prefetch_async() for _ in range(3)])
+
+    def step():
+        if flush is not None:
+            flush.fill_(0.0)
+        out = trainer.train_batch(pend.popleft())
+        pend.append(trainer.prefetch_async())
+        return out
+
+    for _ in range(warmup):
+        step()
+    torch.cuda.synchronize(); ps_dist.barrier()
+    cs = ClockSampler(clock_dev) if clock_dev is not None else None
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        loss = step()[0]
+    e1.record()
+    torch.cuda.synchronize(); ps_dist.barrier()
+    ms = ps_dist.max_over_ranks(e0.elapsed_time(e1) / steps)
+    _drain(pend)
+    return {"ms_per_step": round(ms, 4), "value": round(3 * trainer.batch_size * world / (ms * 1e-3), 1), "unit": UNIT, "steps": steps,
+            "warmup": warmup, "final_loss": float(loss), "clocks": cs.stop() if cs else None}
+
+
+def small_config_leg(name, local, steps=100, warmup=20):
+    """The reference's own default configuration (T=3, batch 128, 512-d: BASELINE.json configs[0] / configs[1] stand-ins)
+    through the drop-in trainer on one GPU; a 256 MB buffer is written between steps (the working set fits in L2)."""
+    import ps_synth
+    import pinsage_training as pst
+    wl = WORKLOADS[name]
+    g = ps_synth.make_graph(wl["n_tracks"], wl["n_cols"], wl["n_edges"], seed=1234, device="cuda")
+    feats = ps_synth.features(wl["n_tracks"], wl["din"], seed=1, device="cuda")
+    positives = ps_synth.cooccurrence_positives(g.device().indptr, g.device().indices, wl["n_tracks"], wl["n_pos"], seed=2)
+    cwd, tmp = os.getcwd(), tempfile.mkdtemp(prefix="psbench_")
+    os.chdir(tmp); os.makedirs("runs", exist_ok=True)
+    try:
+        trainer = pst.PinSage(g, wl["n_tracks"], feats, positives, log=False, load_save=False)
+    finally:
+        os.chdir(cwd)
+    trainer.T = wl["T"]; trainer.model.T = wl["T"]; trainer.batch_size = wl["batch"]
+    flush = torch.empty(64 << 20, dtype=torch.float32, device="cuda")
+    out = train_leg(trainer, steps, warmup, 1, clock_dev=local, flush=flush)
+    trainer.close()
+    out["config"] = workload_config(name, wl, 1)
+    return out
+
+
+def measure_tf32_peak():
+    """Dense TF32 GEMM rate of this GPU (cuBLAS through torch.matmul on fp32 8192^3 with allow_tf32): the tensor-pipe
+    denominator of the 3xTF32 GEMMs, which MEASURED_PEAKS.json (bf16 only) does not hold."""
+    old = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = True
+    try:
+        n = 8192
+        a = torch.randn(n, n, device="cuda"); b = torch.randn(n, n, device="cuda")
+        for _ in range(3):
+            a @ b
+        best, evs = 1e9, []
+        for _ in range(10):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); a @ b; e1.record(); evs.append((e0, e1))
+        torch.cuda.synchronize()
+        best = min(e0.elapsed_time(e1) for e0, e1 in evs)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        reps = 150
+        for _ in range(reps):
+            a @ b
+        e1.record(); torch.cuda.synchronize()
+        return {"tf32_tflops_burst": round(2 * n ** 3 / (best * 1e-3) / 1e12, 1),
+                "tf32_tflops_sustained": round(2 * n ** 3 * reps / (e0.elapsed_time(e1) * 1e-3) / 1e12, 1),
+                "how": "torch.matmul fp32 8192^3, allow_tf32: best of 10 (burst), 150 back to back (sustained)"}
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = old
+
 
 def run_ours(args, wl):
     import ps_dist
@@ -454,6 +598,57 @@ def run_ours(args, wl):
                 f.write(tp.key_averages().table(sort_by="cuda_time_total", row_limit=60, max_name_column_width=70))
             tp.export_chrome_trace(args.torch_profile + ".trace.json")
 
+    # ---- extra sub-lines (not the headline): strong scaling, online sampling, the cfg5 walker modes, the reference's
+    #      own default configs, full-graph inference on this graph, the TF32 peak ----
+    extra = {}
+    _drain(pending); _drain(pending_e2e)
+    if world > 1 and not args.no_extras:  # fixed GLOBAL batch of wl['batch'] triples (strong scaling)
+        trainer.batch_size = max(1, B // world)
+        leg = train_leg(trainer, args.steps, max(3, args.warmup), world, clock_dev=local if rank == 0 else None)
+        leg["scaling"] = "strong"; leg["global_batch"] = trainer.batch_size * world
+        extra["strong"] = leg
+        trainer.batch_size = B
+    if world == 1 and not args.no_extras:
+        if args.sampling != "online":
+            trainer.online_sampling = True
+            leg = train_leg(trainer, min(args.steps, 10), 3, 1, clock_dev=local)
+            leg["sampling"] = "online: ps_walk_topt (n_hops=500, alpha=0.85) on every layer's frontier inside every step"
+            extra["online_sampling"] = leg
+            trainer.online_sampling = False
+            trainer.prefetch(); torch.cuda.synchronize()  # back to the table
+        modes = {}
+        for flen in (3, 4, 5):  # BASELINE.json configs[4]: 1e8 walks of length 3-5 (deterministic restart), top-50
+            runs = []
+            for rep in range(4):
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                ps_native.walk_topt(gh, all_src, 100 * flen, 0.85, 50, seed=20 + rep, fixed_len=flen, want_i64=False, want_i32=True)
+                e1.record(); torch.cuda.synchronize()
+                if rep:
+                    runs.append(e0.elapsed_time(e1))
+            ms = statistics.median(runs)
+            modes[f"len{flen}"] = {"walks": N * 100, "steps": N * 100 * flen, "T": 50, "ms": round(ms, 3),
+                                   "steps_per_s": round(N * 100 * flen / (ms * 1e-3), 1),
+                                   "frac_of_hbm_algorithmic": round(N * 100 * flen * 28 / (ms * 1e-3) / 1e9 / peaks["hbm_gbs"], 4)}
+        extra["walker_fixed_length"] = modes
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        runs = []
+        for rep in range(3):  # full-graph inference of this graph (configs[3]'s path at cfg3 size): embed all N rows
+            e0.record()
+            emb_all = trainer.model.engine.embed_range(feats, 0, N)
+            e1.record(); torch.cuda.synchronize()
+            runs.append(e0.elapsed_time(e1))
+            del emb_all
+        extra["inference_full_graph"] = {"nodes": N, "ms": round(min(runs[1:]), 3), "nodes_per_s": round(N / (min(runs[1:]) * 1e-3), 1),
+                                         "how": "Engine.embed_range(0, N): layer-wise, 2 layers, T=50 (bench.py --mode infer runs configs[3] itself)"}
+        peaks.update(measure_tf32_peak())
+    if world == 1 and not args.no_extras:
+        for name in ("cfg1", "cfg2"):
+            if name != args.workload:
+                extra[name] = small_config_leg(name, local)
+
+    trainer.close()
+
     line = {"metric": METRIC, "value": round(value, 1), "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": round(step_ms, 3), "wall_ms_per_step": round(wall_ms, 3),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -471,16 +666,19 @@ def run_ours(args, wl):
     if ps_engine._PREP_TIMING is not None and ps_engine._PREP_TIMING["n"]:
         t = ps_engine._PREP_TIMING
         line["prep_timing_ms"] = {k: round(v * 1e3 / t["n"], 3) for k, v in t.items() if k != "n"}
+    line["extra"] = extra
     if rank == 0:
         line["roofline"] = roofline_from_profile(prof, args.steps, peaks)
+        line["peaks"] = peaks
         if world == 1 and not args.no_cpu_baseline:
             os.sched_setaffinity(0, allowed_cpus)
             torch.set_num_threads(host_threads)
             Bc = wl["ref_batch"]
             cpu_batches = [pst.sample_batch(ids_cpu, pos_cpu, Bc, nbhds_cpu, hard_negatives=False)[0].numpy() for _ in range(3)]
-            cv, cs = cpu_train_baseline(feats.cpu(), nbhds_cpu, (din, 512, 128), L, T, cpu_batches, warmup=1)
+            cv, cs, ct = cpu_train_baseline(feats.cpu(), nbhds_cpu, (din, 512, 128), L, T, cpu_batches, warmup=1, budget_s=20.0)
             line["cpu_baseline"] = {"value": round(cv, 3), "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
-                                    "sample": f"2 timed steps (1 warm-up) of {Bc} triples (3*{Bc} nodes) on the same {N}-track graph, T={T}; {cs:.2f} s/step"}
+                                    "sample": f"{ct} timed steps (1 warm-up) of {Bc} triples (3*{Bc} nodes) on the same {N}-track graph, T={T}; {cs:.2f} s/step"}
+            line["walk"]["cpu_baseline"] = cpu_walk_baseline(g.indptr.numpy(), g.indices.numpy(), N)
         print(json.dumps(line), flush=True)
     ps_dist.barrier()
     ps_dist.shutdown()
@@ -558,6 +756,7 @@ def main():
     ap.add_argument("--setup-steps", type=int, default=8, help="extra untimed steps before the W warm-up steps (allocator steady state)")
     ap.add_argument("--exchange", action="store_true", help="infer mode: all-gather layer outputs instead of recomputing the closure")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the `extra` sub-lines (strong scaling, online sampling, walker modes, cfg1 / cfg2, TF32 peak)")
     ap.add_argument("--tc-waves", type=int, default=0, help="override ps_gemm_tc_waves (development)")
     ap.add_argument("--gemm-reserve-sms", type=int, default=0, help="ps_gemm_tc_reserve_sms: SMs the persistent GEMMs leave free (development)")
     ap.add_argument("--torch-profile", default=None, help="write a torch.profiler kernel table of 3 extra steps here")
