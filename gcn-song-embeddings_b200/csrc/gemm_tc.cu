@@ -45,6 +45,8 @@ struct TcArgs {
     int64_t mt, nt, zs;  // work grid: M tiles x N tiles x K splits
     const uint8_t* bpack;  // BPACK kernels: hi/lo images of the Q operand, one [2][BN x 128 B] block per (n-tile, k-block)
     uint32_t* mask; int64_t ldm;  // optional sign mask of the activation, one bit per output element (ldm in 32-bit words)
+    float* p_colsum;  // weight-gradient kernels (MN-major x MN-major): p_colsum[i] += sum_r P(i, r) -- the bias gradient, from the
+                      // elements the producers already hold for the hi/lo split (replaces a separate pass over P)
 };
 
 // ---------------------------------------------------------------- PTX wrappers
@@ -473,6 +475,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(TcArgs a) {
             issue(0);
             advance();
         }
+        float4 csum = make_float4(0.f, 0.f, 0.f, 0.f);  // this thread's 4 P columns summed over the work item's k range
         for (int64_t w = blockIdx.x; w < total_work; w += gridDim.x) {
             const Work wk = decode_work(a, w, BN);
             for (int kb = 0; kb < wk.num_kb; ++kb) {
@@ -483,6 +486,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(TcArgs a) {
                 for (int j = 0; j < OpA::NJ; ++j) {
                     float4* hp = reinterpret_cast<float4*>(st + offa + j * OpA::kStep);
                     const float4 v = *hp;
+                    csum.x += v.x; csum.y += v.y; csum.z += v.z; csum.w += v.w;  // rows k >= K were zero-filled
                     float4 l;
                     l.x = v.x - __uint_as_float(__float_as_uint(v.x) & kHiMask); l.y = v.y - __uint_as_float(__float_as_uint(v.y) & kHiMask);
                     l.z = v.z - __uint_as_float(__float_as_uint(v.z) & kHiMask); l.w = v.w - __uint_as_float(__float_as_uint(v.w) & kHiMask);
@@ -506,6 +510,14 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(TcArgs a) {
                     issue(stage);
                     advance();
                 }
+            }
+            if (a.p_colsum != nullptr) {  // every (m-tile, k-split) reads its P slice once per n-tile: count n-tile 0 only
+                const int64_t i = wk.m0 + (t % OpA::C4) * 4;
+                if (wk.n0 == 0 && i < a.M) {  // M % 4 == 0 on this path: a float4 of columns is all-or-nothing
+                    atomicAdd(a.p_colsum + i, csum.x); atomicAdd(a.p_colsum + i + 1, csum.y);
+                    atomicAdd(a.p_colsum + i + 2, csum.z); atomicAdd(a.p_colsum + i + 3, csum.w);
+                }
+                csum = make_float4(0.f, 0.f, 0.f, 0.f);
             }
         }
     } else if (warp >= 8) {
@@ -768,8 +780,9 @@ int ps_gemm_tc_launch(const float* P, int64_t ldp, int p_kmajor, const int32_t* 
                       const float* Q, int64_t ldq, int q_kmajor, const int32_t* q_rows,
                       float* C, int64_t ldc, int64_t M, int64_t N, int64_t K,
                       const float* bias, int act, int l2norm, float* norm_out, int accumulate, int splits,
-                      uint32_t* mask, int64_t ldm, cudaStream_t stream) {
-    if (M <= 0 || N < 64 || K < 32) return PS_ERR_UNSUPPORTED;                 // tiny problems: not worth a 128-wide tile
+                      uint32_t* mask, int64_t ldm, float* p_colsum, cudaStream_t stream) {
+    if (M <= 0 || N < 64 || K < 32) return PS_ERR_UNSUPPORTED;
+    if (p_colsum != nullptr && (p_kmajor || q_kmajor || !accumulate)) return PS_ERR_UNSUPPORTED;  // weight-gradient form only                 // tiny problems: not worth a 128-wide tile
     if (mask != nullptr && (N % 32 != 0 || (act != 1 && act != 2) || l2norm)) return PS_ERR_UNSUPPORTED;
     if ((ldp | ldq | ldc | N) % 4 != 0) return PS_ERR_UNSUPPORTED;
     if ((p_kmajor || q_kmajor) && K % 4 != 0) return PS_ERR_UNSUPPORTED;
@@ -788,7 +801,7 @@ int ps_gemm_tc_launch(const float* P, int64_t ldp, int p_kmajor, const int32_t* 
     if (!accumulate && K > 4 * kMaxChainK) return PS_ERR_UNSUPPORTED;
     if (accumulate && ps_ceil_div(K, splits < 1 ? 1 : splits) > kMaxChainK) splits = static_cast<int>(ps_ceil_div(K, kMaxChainK));
     const int BN = (N > 128) ? 256 : 128;
-    TcArgs a{P, ldp, p_rows, Q, ldq, q_rows, C, ldc, M, N, K, bias, norm_out, act, l2norm, accumulate, 0, 0, 0, 0, nullptr, mask, ldm};
+    TcArgs a{P, ldp, p_rows, Q, ldq, q_rows, C, ldc, M, N, K, bias, norm_out, act, l2norm, accumulate, 0, 0, 0, 0, nullptr, mask, ldm, p_colsum};
     const int64_t num_kb = ps_ceil_div(K, BK);
     if (splits < 1) splits = 1;
     a.kb_per_split = static_cast<int>(ps_ceil_div(num_kb, splits));

@@ -99,7 +99,85 @@ __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, 
     }
 }
 
+// Training diagnostics of PinSage.train_batch (pinsage_training.py:200-212), which the reference computes every step
+// with ~25 framework ops: (1) the cosine triplet loss of the RAW node features of the batch,
+// mean_i max(d(a,p) - d(a,n) + margin, 0), d = 1 - cos, on F.normalize'd rows; (2) the batch variance of the query
+// embeddings, sum_ij (h_ij - mean_j)^2 / (B - 1).  One warp per triple / one CTA per 32 columns.
+__global__ void __launch_bounds__(kWarps * 32)
+feat_triplet_kernel(const float* __restrict__ feats, int64_t ld, int d, const int64_t* __restrict__ batch, int64_t B,
+                    float margin, float* __restrict__ out) {
+    const int lane = threadIdx.x & 31;
+    const int64_t i = static_cast<int64_t>(blockIdx.x) * kWarps + (threadIdx.x >> 5);
+    if (i >= B) return;
+    const float* a = feats + batch[3 * i] * ld;
+    const float* p = feats + batch[3 * i + 1] * ld;
+    const float* n = feats + batch[3 * i + 2] * ld;
+    float aa = 0.f, pp = 0.f, nn = 0.f, ap = 0.f, an = 0.f;
+    for (int c = lane * 4; c < d; c += 128) {
+        const float4 x = ps_ldg4(a + c), y = ps_ldg4(p + c), z = ps_ldg4(n + c);
+        aa += x.x * x.x + x.y * x.y + x.z * x.z + x.w * x.w;
+        pp += y.x * y.x + y.y * y.y + y.z * y.z + y.w * y.w;
+        nn += z.x * z.x + z.y * z.y + z.z * z.z + z.w * z.w;
+        ap += x.x * y.x + x.y * y.y + x.z * y.z + x.w * y.w;
+        an += x.x * z.x + x.y * z.y + x.z * z.z + x.w * z.w;
+    }
+    aa = ps_warp_sum(aa); pp = ps_warp_sum(pp); nn = ps_warp_sum(nn); ap = ps_warp_sum(ap); an = ps_warp_sum(an);
+    if (lane == 0) {
+        // F.normalize (eps 1e-12), then cosine_similarity of the unit rows (eps 1e-8 on each norm)
+        const float na = fmaxf(sqrtf(aa), 1e-12f), np_ = fmaxf(sqrtf(pp), 1e-12f), nn_ = fmaxf(sqrtf(nn), 1e-12f);
+        const float ua = fmaxf(sqrtf(aa) / na, 1e-8f), up = fmaxf(sqrtf(pp) / np_, 1e-8f), un = fmaxf(sqrtf(nn) / nn_, 1e-8f);
+        const float cap = ap / (na * np_) / (ua * up), can = an / (na * nn_) / (ua * un);
+        atomicAdd(out, fmaxf((1.f - cap) - (1.f - can) + margin, 0.f) / static_cast<float>(B));
+    }
+}
+
+__global__ void __launch_bounds__(256)
+batch_variance_kernel(const float* __restrict__ emb, int64_t ld, int d, const int32_t* __restrict__ triples, int64_t B,
+                      float* __restrict__ out) {
+    __shared__ float part[8][33];
+    const int lx = threadIdx.x & 31, ly = threadIdx.x >> 5;
+    const int col = blockIdx.x * 32 + lx;
+    float s = 0.f;
+    if (col < d)
+        for (int64_t r = ly; r < B; r += 8) s += __ldg(emb + static_cast<int64_t>(__ldg(triples + 3 * r)) * ld + col);
+    part[ly][lx] = s;
+    __syncthreads();
+    float mean = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) mean += part[k][lx];
+    mean /= static_cast<float>(B);
+    __syncthreads();
+    float q = 0.f;
+    if (col < d)
+        for (int64_t r = ly; r < B; r += 8) {
+            const float x = __ldg(emb + static_cast<int64_t>(__ldg(triples + 3 * r)) * ld + col) - mean;
+            q = fmaf(x, x, q);
+        }
+    part[ly][lx] = q;
+    __syncthreads();
+    if (ly == 0) {
+#pragma unroll
+        for (int k = 1; k < 8; ++k) q += part[k][lx];
+        q = ps_warp_sum(q);
+        if (lx == 0) atomicAdd(out, q / static_cast<float>(B - 1));
+    }
+}
+
 }  // namespace
+
+extern "C" int ps_train_diagnostics(const float* feats, int64_t ld_feats, int d_feat, const int64_t* batch, int64_t B,
+                                    const float* emb, int64_t ld_emb, int d_emb, const int32_t* triples, float feat_margin,
+                                    float* out2, ps_stream_t stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    PS_REQUIRE(feats && batch && emb && triples && out2, "null pointer");
+    PS_REQUIRE(B > 0 && d_feat > 0 && d_feat % 4 == 0 && ld_feats % 4 == 0 && d_emb > 0, "bad shape");
+    PS_CUDA_CHECK(cudaMemsetAsync(out2, 0, 2 * sizeof(float), stream));
+    feat_triplet_kernel<<<static_cast<unsigned>(ps_ceil_div(B, kWarps)), kWarps * 32, 0, stream>>>(feats, ld_feats, d_feat, batch, B, feat_margin, out2);
+    PS_LAUNCH_CHECK();
+    batch_variance_kernel<<<static_cast<unsigned>(ps_ceil_div(d_emb, 32)), 256, 0, stream>>>(emb, ld_emb, d_emb, triples, B, out2 + 1);
+    PS_LAUNCH_CHECK();
+    return PS_OK;
+}
 
 extern "C" int ps_count_triples(const int32_t* triples, int64_t B, int64_t U, int32_t* dup_counts, ps_stream_t stream_) {
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);

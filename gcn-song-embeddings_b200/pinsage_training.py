@@ -199,7 +199,9 @@ class PinSage():
 
         self.lr = 1e-4
         self.decay = 0.95
-        self.optimizer = torch.optim.Adam(self.model.parameters(), lr=self.lr)
+        # torch.optim.Adam's interface and state_dict format, one fused kernel per step (ps_optim.FlatAdam)
+        from ps_optim import FlatAdam
+        self.optimizer = FlatAdam(self.model.parameters(), lr=self.lr, engine=self.model.engine)
         self.scheduler = torch.optim.lr_scheduler.ExponentialLR(self.optimizer, self.decay)
         self.margin = 1e-5
         self.epochs = 30
@@ -318,13 +320,10 @@ class PinSage():
         ev = torch.cuda.Event()
         ev.record()
         done.append(ev)
-        if self.diagnostics:
-            with torch.no_grad():
-                norm = F.normalize
-                node_feat_loss = COSINE_TRIPLET_LOSS(norm(feats[batch[:, 0], :], dim=1),
-                                                     norm(feats[batch[:, 1], :], dim=1),
-                                                     norm(feats[batch[:, 2], :], dim=1))
-                variance = batch_variance(emb[triples[:, 0].long()])
+        if self.diagnostics:  # node-feature triplet loss + batch variance (pinsage_training.py:200-212) in one call
+            diag = torch.empty(2, dtype=torch.float32, device="cuda")
+            ps_native.train_diagnostics(feats, batch, emb, triples, COSINE_TRIPLET_LOSS.margin, diag)
+            node_feat_loss, variance = diag[0], diag[1]
         else:
             node_feat_loss = variance = torch.zeros((), device="cuda")
         return loss[0], node_feat_loss, variance

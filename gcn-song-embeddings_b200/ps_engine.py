@@ -321,9 +321,7 @@ class Engine:
         d_a1 = torch.empty_like(a1)
         nat.gemm(d_out, m.G2.weight, d_a1, n_top, do, do, q_kmajor=False)
         nat.leaky_bwd(a1, d_a1)
-        nat.gemm(d_a1, h_top, grads["G1.weight"], do, do, n_top, p_kmajor=False, q_kmajor=False,
-                 accumulate=True, splits=_splits_for(do, do, n_top))
-        nat.colsum(d_a1, grads["G1.bias"])
+        nat.gemm_wgrad(d_a1, h_top, grads["G1.weight"], do, do, n_top, splits=_splits_for(do, do, n_top), bias_grad=grads["G1.bias"])
         d_h = torch.empty((n_top, do), dtype=torch.float32, device="cuda")
         nat.gemm(d_a1, m.G1.weight, d_h, n_top, do, do, q_kmajor=False)
 
@@ -335,9 +333,10 @@ class Engine:
             pre = f"conv_layers.{l}."
             d_pre = torch.empty((lp.n, do), dtype=torch.float32, device="cuda")
             nat.norm_leaky_bwd(h, norm, d_h, d_pre)
-            nat.gemm(d_pre, cat, grads[pre + "W.weight"], do, din + dh, lp.n, p_kmajor=False, q_kmajor=False,
-                     accumulate=True, splits=_splits_for(do, din + dh, lp.n), tag=f"gemm_w_wgrad_l{l}")
-            nat.colsum(d_pre, grads[pre + "W.bias"])
+            # weight AND bias gradient in one call: the bias gradient (column sums of the upstream gradient) comes from
+            # the operand tiles the GEMM's producers already hold
+            nat.gemm_wgrad(d_pre, cat, grads[pre + "W.weight"], do, din + dh, lp.n, splits=_splits_for(do, din + dh, lp.n),
+                           bias_grad=grads[pre + "W.bias"], tag=f"gemm_w_wgrad_l{l}")
             # Backward of the aggregation.  d_cat[:, din:] = d_pre . W[:, din:] is linear in d_pre, so the weighted
             # segment sum runs on the do-wide d_pre rows (4x fewer gathered bytes than the dh-wide d_cat rows, and
             # d_pre fits in L2) and ONE GEMM applies the W block per z-row, with leaky'(z) fused into its store:
@@ -348,9 +347,8 @@ class Engine:
                               chunk_row=lp.chunk_row, apply_leaky=False, tag=f"aggregate_bwd_l{l}")
             nat.gemm(s_buf, conv.W.weight.detach()[:, din:], z, lp.nz, dh, do, q_kmajor=False, act=2, mask=zmask,
                      tag=f"gemm_agg_dgrad_l{l}")  # z := dZ_pre (leaky' from the recorded sign bits, else from z itself)
-            nat.gemm(z, h_in, grads[pre + "Q.weight"], dh, din, lp.nz, p_kmajor=False, q_kmajor=False,
-                     q_rows=lp.zrows, accumulate=True, splits=_splits_for(dh, din, lp.nz), tag=f"gemm_q_wgrad_l{l}")
-            nat.colsum(z, grads[pre + "Q.bias"])
+            nat.gemm_wgrad(z, h_in, grads[pre + "Q.weight"], dh, din, lp.nz, x_rows=lp.zrows, splits=_splits_for(dh, din, lp.nz),
+                           bias_grad=grads[pre + "Q.bias"], tag=f"gemm_q_wgrad_l{l}")
             if l > 0:
                 d_h = torch.empty((lp.nz, din), dtype=torch.float32, device="cuda")
                 nat.gemm(z, conv.Q.weight, d_h, lp.nz, din, dh, q_kmajor=False, tag=f"gemm_q_dgrad_l{l}")

@@ -36,6 +36,7 @@ _SIGNATURES = {
     "ps_gemm_ex": ([c_void_p, c_int64, c_int, c_void_p, c_void_p, c_int64, c_int, c_void_p, c_void_p, c_int64,
                     c_int64, c_int64, c_int64, c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_void_p, c_int64, c_void_p], c_int),
     "ps_gemm_mask_supported": ([c_int64, c_int64, c_int64], c_int),
+    "ps_gemm_wgrad": ([c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int64, c_int, c_void_p, c_void_p], c_int),
     "ps_gemm_tc_pack": ([c_int], c_int),
     "ps_gemm_tc_waves": ([c_int], c_int),
     "ps_gemm_tc_reserve_sms": ([c_int], c_int),
@@ -65,6 +66,7 @@ _SIGNATURES = {
     "ps_sample_batch": ([c_void_p, c_int64, c_void_p, c_int64, c_int, c_uint64, c_uint64, c_void_p, c_void_p, c_int64,
                          c_void_p, c_void_p], c_int),
     "ps_topk_rows": ([c_void_p, c_int64, c_int64, c_int64, c_int, c_void_p, c_void_p, c_void_p], c_int),
+    "ps_train_diagnostics": ([c_void_p, c_int64, c_int, c_void_p, c_int64, c_void_p, c_int64, c_int, c_void_p, c_float, c_void_p, c_void_p], c_int),
     "ps_adam_step": ([c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_float, c_float, c_float, c_float, c_int64,
                       c_float, c_void_p], c_int),
 }
@@ -264,6 +266,14 @@ def _gemm(P, Q, C, M, N, K, p_kmajor, q_kmajor, p_rows, q_rows, bias, act, l2nor
                            _p(mask, torch.int32), _ld(mask) if mask is not None else 0, _stream()))
 
 
+def gemm_wgrad(dY, X, dW, M, N, K, *, x_rows=None, splits=1, bias_grad=None, tag="gemm_wgrad"):
+    """ps_gemm_wgrad: dW[M,N] += dY[:K,:M]^T X[rows][:K,:N] and bias_grad[M] += colsum(dY) in one call."""
+    with _Timed(tag, 2.0 * M * N * K, 4.0 * (M * K + N * K + M * N)):
+        check(lib().ps_gemm_wgrad(_p(dY, torch.float32), _ld(dY), _p(X, torch.float32), _ld(X), _p(x_rows, torch.int32),
+                                  _p(dW, torch.float32), _ld(dW), int(M), int(N), int(K), int(splits),
+                                  _p(bias_grad, torch.float32), _stream()))
+
+
 def gemm_backend(mode: int) -> int:
     """0 = tcgen05 3xTF32 (default), 1 = CUDA-core fp32; returns the previous mode."""
     return lib().ps_gemm_backend(int(mode))
@@ -415,6 +425,13 @@ def topk_rows(x, k):
     idx = torch.empty((n, k), dtype=torch.int64, device="cuda")
     check(lib().ps_topk_rows(_p(x, torch.float32), _ld(x), int(n), int(m), int(k), _p(val), _p(idx), _stream()))
     return val, idx
+
+
+def train_diagnostics(feats, batch, emb, triples, feat_margin, out2):
+    """ps_train_diagnostics: out2 = [feature triplet loss, batch variance of the query embeddings]."""
+    check(lib().ps_train_diagnostics(_p(feats, torch.float32), _ld(feats), int(feats.shape[1]), _p(batch, torch.int64), int(batch.shape[0]),
+                                     _p(emb, torch.float32), _ld(emb), int(emb.shape[1]), _p(triples, torch.int32), float(feat_margin),
+                                     _p(out2, torch.float32), _stream()))
 
 
 def adam_step(param, grad, exp_avg, exp_avg_sq, lr, beta1, beta2, eps, step, grad_scale=1.0):

@@ -205,6 +205,22 @@ int ps_sample_batch(const int64_t* positives, int64_t P, const int64_t* all_ids,
 int ps_topk_rows(const float* x, int64_t ld, int64_t n_rows, int64_t n_cols, int k,
                  float* out_val, int64_t* out_idx, ps_stream_t stream);
 
+/* ---- weight + bias gradient of a Linear layer in one call (AddmmBackward of nn.Linear, pinsage_model.py:201,208,259):
+ *      C[i,j] += sum_r P[r*ldp + i] * Q[rows(r)*ldq + j]   (dW += dY^T X, optional row gather on X)
+ *      p_colsum[i] += sum_r P[r*ldp + i]                   (db += colsum(dY); NULL = skip)
+ *      splits = split-K factor (partials combined with fp32 atomics). ---- */
+int ps_gemm_wgrad(const float* P, int64_t ldp, const float* Q, int64_t ldq, const int32_t* q_rows,
+                  float* C, int64_t ldc, int64_t M, int64_t N, int64_t K, int splits, float* p_colsum,
+                  ps_stream_t stream);
+
+/* ---- per-step training diagnostics of PinSage.train_batch (pinsage_training.py:200-212): out2[0] = cosine triplet
+ *      loss (margin feat_margin, mean) of the F.normalize'd raw feature rows of the batch's (q, pos, neg) ids
+ *      (batch int64 [B,3]); out2[1] = batch variance of the query embeddings emb[triples[:,0]] (batch_variance,
+ *      pinsage_training.py:99-103: sum of squared deviations from the column means / (B - 1)). ---- */
+int ps_train_diagnostics(const float* feats, int64_t ld_feats, int d_feat, const int64_t* batch, int64_t B,
+                         const float* emb, int64_t ld_emb, int d_emb, const int32_t* triples, float feat_margin,
+                         float* out2, ps_stream_t stream);
+
 /* ---- K13: Adam step on a flat fp32 parameter buffer (torch.optim.Adam defaults:
  *      betas, eps, no weight decay, no amsgrad; pinsage_training.py:147,191).
  *      step is the 1-based step count used for bias correction. ---- */

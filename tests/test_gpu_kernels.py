@@ -335,3 +335,70 @@ def test_sample_batch_uniform():
     for h in (neg, row):
         exp = h.sum() / 64
         assert ((h - exp) ** 2 / exp).sum() < 130  # chi2(63) 99.99th percentile ~ 115
+
+
+@pytest.mark.parametrize("M,N,K,splits,gather", [(512, 256, 20_000, 74, True), (128, 768, 13_375, 53, False), (128, 128, 741, 3, False),
+                                                 (96, 64, 10_000, 7, True), (36, 20, 300, 1, False)])
+def test_gemm_wgrad_with_bias_gradient(nat, backend, M, N, K, splits, gather):
+    """ps_gemm_wgrad: dW += dY^T X[rows] and db += colsum(dY) in one call (AddmmBackward of nn.Linear,
+    pinsage_model.py:201,208,259); the bias gradient comes out of the GEMM's own operand tiles on the tcgen05 path."""
+    torch.manual_seed(M + K)
+    dY = torch.randn(K, M, device="cuda")
+    X = torch.randn(3000 if gather else K, N, device="cuda")
+    rows = torch.randint(0, 3000, (K,), device="cuda", dtype=torch.int32) if gather else None
+    dW = torch.full((M, N), 0.5, device="cuda"); db = torch.full((M,), -1.0, device="cuda")
+    nat.gemm_wgrad(dY, X, dW, M, N, K, x_rows=rows, splits=splits, bias_grad=db)
+    Xg = X[rows.long()] if gather else X
+    assert rel(dW, 0.5 + dY.double().t() @ Xg.double()) < 2e-5
+    assert rel(db, -1.0 + dY.double().sum(0)) < 2e-5
+    dW2 = torch.zeros((M, N), device="cuda")
+    nat.gemm_wgrad(dY, X, dW2, M, N, K, x_rows=rows, splits=splits)  # bias gradient not wanted
+    assert rel(dW2, dY.double().t() @ Xg.double()) < 2e-5
+
+
+def test_train_diagnostics_match_torch(nat):
+    """ps_train_diagnostics == the reference's per-step diagnostics (pinsage_training.py:200-212): the cosine triplet
+    loss of the raw batch features and batch_variance of the query embeddings."""
+    import pinsage_training as pst
+    torch.manual_seed(3)
+    for B, din, do in ((128, 512, 128), (1024, 256, 128), (7, 64, 32)):
+        feats = torch.randn(5000, din, device="cuda")
+        batch = torch.randint(0, 5000, (B, 3), device="cuda")
+        emb = torch.randn(3 * B, do, device="cuda")
+        triples = torch.randint(0, 3 * B, (B, 3), device="cuda", dtype=torch.int32)
+        out = torch.empty(2, device="cuda")
+        nat.train_diagnostics(feats, batch, emb, triples, pst.COSINE_TRIPLET_LOSS.margin, out)
+        norm = torch.nn.functional.normalize
+        want_l = pst.COSINE_TRIPLET_LOSS(norm(feats[batch[:, 0]], dim=1), norm(feats[batch[:, 1]], dim=1), norm(feats[batch[:, 2]], dim=1))
+        want_v = pst.batch_variance(emb[triples[:, 0].long()])
+        assert abs(float(out[0]) - float(want_l)) < 1e-5 * max(1.0, abs(float(want_l)))
+        assert abs(float(out[1]) - float(want_v)) < 1e-4 * abs(float(want_v))
+
+
+def test_flat_adam_equals_torch_adam():
+    """ps_optim.FlatAdam (one fused kernel per step) == torch.optim.Adam step for step, with torch's state_dict format
+    in both directions (the reference checkpoints `optimizer.state_dict()`, pinsage_training.py:288-295) and the
+    scheduler driving param_groups[0]['lr']."""
+    from ps_optim import FlatAdam
+    torch.manual_seed(0)
+    a = torch.nn.Sequential(torch.nn.Linear(64, 96), torch.nn.Linear(96, 8, bias=False)).cuda()
+    b = torch.nn.Sequential(torch.nn.Linear(64, 96), torch.nn.Linear(96, 8, bias=False)).cuda()
+    b.load_state_dict(a.state_dict())
+    oa, ob = torch.optim.Adam(a.parameters(), lr=1e-3), FlatAdam(b.parameters(), lr=1e-3)
+    sa, sb = torch.optim.lr_scheduler.ExponentialLR(oa, 0.9), torch.optim.lr_scheduler.ExponentialLR(ob, 0.9)
+    for step in range(6):
+        x = torch.randn(32, 64, device="cuda")
+        for m, o in ((a, oa), (b, ob)):
+            o.zero_grad(); m(x).pow(2).mean().backward(); o.step()
+        if step % 2:
+            sa.step(); sb.step()
+        if step == 2:  # checkpoint round trip through torch's format, both ways
+            sd_b, sd_a = ob.state_dict(), oa.state_dict()
+            assert set(sd_b) == set(sd_a) and set(sd_b["state"][0]) == set(sd_a["state"][0])
+            ob2 = FlatAdam(b.parameters(), lr=1e-3); ob2.load_state_dict(sd_b)
+            oa2 = torch.optim.Adam(a.parameters(), lr=1e-3); oa2.load_state_dict(sd_b)   # torch reads ours
+            ob2.load_state_dict(sd_a)                                                    # we read torch's
+            assert ob2._t == 3 and rel(ob2._flat_m, ob._flat_m) < 1e-6
+    for pa, pb in zip(a.parameters(), b.parameters()):
+        assert rel(pb, pa) < 1e-6
+    assert oa.param_groups[0]["lr"] == ob.param_groups[0]["lr"]
