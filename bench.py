@@ -507,7 +507,8 @@ def run_ours(args, wl):
 
     # ---- timed region: K steps, device-resident inputs ----
     sampler = ClockSampler(local) if rank == 0 else None
-    ps_native.profiler = ps_native.Profiler()
+    ps_native.profiler = ps_native.Profiler()  # calls composed from Python (the online walker)
+    ps_native.native_profile(True)             # the launches inside ps_train_step (CUDA events on the launching stream)
     launches0 = ps_native.launch_count
     t0 = torch.cuda.Event(enable_timing=True); t1 = torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize(); ps_dist.barrier()
@@ -527,6 +528,7 @@ def run_ours(args, wl):
     host_ms = {k: round(v * 1e3 / args.steps, 3) for k, v in host.items()}
     clocks = sampler.stop() if sampler else None
     prof = ps_native.profiler.summary(); ps_native.profiler = None
+    prof.update(ps_native.native_profile_summary()); ps_native.native_profile(False)
     step_ms = ps_dist.max_over_ranks(max(dev_ms, 0.0) / args.steps)
     wall_ms = ps_dist.max_over_ranks(wall * 1e3 / args.steps)
     # device events bracket the region; the wall clock is reported beside it (host-side frontier construction

@@ -313,16 +313,18 @@ class PinSage():
             done = self._steps_in_flight = deque()
         while self.max_steps_in_flight and len(done) >= self.max_steps_in_flight:
             done.popleft().synchronize()
-        loss, emb, triples = self.model.engine.train_step(feats, prep, self.margin, self.reference_compat)
+        loss, emb, triples = self.model.engine.train_step(feats, prep, self.margin, self.reference_compat, diagnostics=bool(self.diagnostics))
         if self._grad_sync is not None:
             self._grad_sync()
         self.optimizer.step()
         ev = torch.cuda.Event()
         ev.record()
         done.append(ev)
-        if self.diagnostics:  # node-feature triplet loss + batch variance (pinsage_training.py:200-212) in one call
-            diag = torch.empty(2, dtype=torch.float32, device="cuda")
-            ps_native.train_diagnostics(feats, batch, emb, triples, COSINE_TRIPLET_LOSS.margin, diag)
+        if self.diagnostics:  # node-feature triplet loss + batch variance (pinsage_training.py:200-212)
+            diag = self.model.engine.last_diag  # computed inside the fused step call
+            if diag is None:
+                diag = torch.empty(2, dtype=torch.float32, device="cuda")
+                ps_native.train_diagnostics(feats, batch, emb, triples, COSINE_TRIPLET_LOSS.margin, diag)
             node_feat_loss, variance = diag[0], diag[1]
         else:
             node_feat_loss = variance = torch.zeros((), device="cuda")

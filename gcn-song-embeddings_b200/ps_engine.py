@@ -357,7 +357,7 @@ class Engine:
                 nat.scatter_add_rows(d_self, lp.self_rows, d_h, din)
         return grads
 
-    def zero_grads(self):
+    def zero_grads(self, zero: bool = True):
         """Dict name -> zeroed gradient tensor.  All gradients are views into ONE flat fp32
         buffer (self.flat_grad) installed as the parameters' .grad, so the data-parallel
         exchange is a single allreduce and zeroing a single memset."""
@@ -366,7 +366,7 @@ class Engine:
         flat = getattr(self, "flat_grad", None)
         if flat is None or flat.numel() != total or flat.device != params[0][1].device:
             flat = self.flat_grad = torch.zeros(total, dtype=torch.float32, device=params[0][1].device)
-        else:
+        elif zero:
             flat.zero_()
         grads, off = {}, 0
         for name, p in params:
@@ -422,15 +422,21 @@ class Engine:
                 side.synchronize(); timing["plan_drain"] += time.perf_counter() - t3; timing["n"] += 1
         return Prepared(batch=batch, triples=triples, plan=plan, counts=counts, ready=ready)
 
-    def train_step(self, feats: torch.Tensor, batch, margin: float, reference_compat: bool = True):
+    def train_step(self, feats: torch.Tensor, batch, margin: float, reference_compat: bool = True, diagnostics: bool = False):
         """Forward of the distinct nodes of a batch, max-margin loss, backward into the parameters' .grad.
         `batch` is an int64 [B,3] tensor or a Prepared from prepare().  Returns (loss [1], embeddings of the
-        distinct nodes [U, out], triples int32 [B,3] indexing them), all on the device."""
+        distinct nodes [U, out], triples int32 [B,3] indexing them), all on the device.  The whole step is ONE host
+        call (ps_train_step, csrc/step.cu); diagnostics=True also leaves [node-feature triplet loss, batch variance]
+        (pinsage_training.py:200-212) in self.last_diag.  PS_PY_STEP=1 composes the same kernels from Python instead
+        (Engine.forward / backward, what model(features, nodeset) + autograd use)."""
         prep = batch if isinstance(batch, Prepared) else self.prepare(batch)
         main = torch.cuda.current_stream()
         main.wait_event(prep.ready)
         for t in prep.tensors():
             t.record_stream(main)  # allocated on the side stream, consumed here
+        if os.environ.get("PS_PY_STEP") != "1":
+            return self._train_step_native(feats, prep, margin, reference_compat, diagnostics)
+        self.last_diag = None
         out, ctx = self.forward(feats, prep.plan, keep=True)
         loss = torch.zeros(1, dtype=torch.float32, device="cuda")
         d_out = torch.zeros_like(out)
@@ -438,6 +444,52 @@ class Engine:
         grads = self.zero_grads()
         self.backward(ctx, d_out, grads)
         return loss, out, prep.triples
+
+    def _train_step_native(self, feats, prep, margin, reference_compat, diagnostics):
+        m = self.model
+        in_dims, dh, do = self._dims()
+        if feats.shape[1] < in_dims[0] or in_dims[0] % 4 or dh % 4 or do % 4:
+            raise ValueError("feature / hidden / output dims must be multiples of 4 and features at least in_dim wide")
+        L = len(prep.plan.layers)
+        if L > nat.PS_MAX_LAYERS:
+            raise ValueError(f"at most {nat.PS_MAX_LAYERS} layers")
+        grads = self.zero_grads(zero=False)  # ps_train_step zeroes the flat buffer itself
+        a = nat.StepArgsC()
+        a.n_layers, a.T, a.in_dim, a.hidden_dim, a.out_dim = L, prep.plan.layers[0].nbz.shape[1], in_dims[0], dh, do
+        a.feats, a.ld_feats = feats.data_ptr(), feats.stride(0)
+        ptr = lambda t: t.data_ptr() if t is not None else None
+        for l, lp in enumerate(prep.plan.layers):
+            c = a.layers[l]
+            c.n, c.nz = lp.n, lp.nz
+            c.self_rows, c.nbz, c.w, c.zrows = ptr(lp.self_rows), ptr(lp.nbz), ptr(lp.w), ptr(lp.zrows)
+            c.seg_off, c.pair_q, c.chunk_off, c.chunk_row = ptr(lp.seg_off), ptr(lp.pair_q), ptr(lp.chunk_off), ptr(lp.chunk_row)
+            conv, pre, q = m.conv_layers[l], f"conv_layers.{l}.", a.params[l]
+            q.Qw, q.Qb, q.Ww, q.Wb = conv.Q.weight.data_ptr(), conv.Q.bias.data_ptr(), conv.W.weight.data_ptr(), conv.W.bias.data_ptr()
+            q.gQw, q.gQb, q.gWw, q.gWb = (grads[pre + k].data_ptr() for k in ("Q.weight", "Q.bias", "W.weight", "W.bias"))
+        a.G1w, a.G1b, a.G2w = m.G1.weight.data_ptr(), m.G1.bias.data_ptr(), m.G2.weight.data_ptr()
+        a.gG1w, a.gG1b, a.gG2w = grads["G1.weight"].data_ptr(), grads["G1.bias"].data_ptr(), grads["G2.weight"].data_ptr()
+        a.triples, a.B = prep.triples.data_ptr(), prep.triples.shape[0]
+        a.dup_counts = prep.counts.data_ptr() if reference_compat else None
+        a.margin, a.feat_margin = float(margin), 0.0001
+        a.flat_grad, a.n_params = self.flat_grad.data_ptr(), self.flat_grad.numel()
+        need = nat.lib().ps_train_step_workspace(a)
+        if need < 0:
+            raise nat.NativeError(f"ps_train_step_workspace: {nat.lib().ps_last_error().decode()}")
+        ws = torch.empty(int(need) + 256, dtype=torch.uint8, device="cuda")
+        base = (ws.data_ptr() + 255) & ~255
+        a.workspace, a.workspace_bytes = base, int(need)
+        out = torch.empty(3 if diagnostics else 1, dtype=torch.float32, device="cuda")  # [loss, feature loss, variance]
+        a.loss_out = out.data_ptr()
+        if diagnostics:
+            a.batch, a.diag_out = prep.batch.data_ptr(), out.data_ptr() + 4
+        emb_ptr = nat.c_void_p()
+        a.emb_out = nat.ctypes.pointer(emb_ptr)
+        nat.train_step(a, launches=10 + 13 * L)
+        n_top = prep.plan.layers[-1].n
+        off = emb_ptr.value - ws.data_ptr()
+        emb = ws[off: off + n_top * do * 4].view(torch.float32).view(n_top, do)
+        self.last_diag = out[1:] if diagnostics else None
+        return out[:1], emb, prep.triples
 
     @torch.no_grad()
     def embed(self, feats: torch.Tensor, nodes: torch.Tensor) -> torch.Tensor:

@@ -71,6 +71,39 @@ _SIGNATURES = {
                       c_float, c_void_p], c_int),
 }
 
+PS_MAX_LAYERS = 8
+
+
+class LayerPlanC(ctypes.Structure):
+    _fields_ = [("n", c_int64), ("nz", c_int64), ("self_rows", c_void_p), ("nbz", c_void_p), ("w", c_void_p), ("zrows", c_void_p),
+                ("seg_off", c_void_p), ("pair_q", c_void_p), ("chunk_off", c_void_p), ("chunk_row", c_void_p)]
+
+
+class LayerParamsC(ctypes.Structure):
+    _fields_ = [(k, c_void_p) for k in ("Qw", "Qb", "Ww", "Wb", "gQw", "gQb", "gWw", "gWb")]
+
+
+class StepArgsC(ctypes.Structure):
+    """ps_step_args of include/pinsage_b200.h."""
+    _fields_ = [("n_layers", ctypes.c_int32), ("T", ctypes.c_int32), ("in_dim", ctypes.c_int32), ("hidden_dim", ctypes.c_int32),
+                ("out_dim", ctypes.c_int32), ("reserved", ctypes.c_int32),
+                ("feats", c_void_p), ("ld_feats", c_int64),
+                ("layers", LayerPlanC * PS_MAX_LAYERS), ("params", LayerParamsC * PS_MAX_LAYERS),
+                ("G1w", c_void_p), ("G1b", c_void_p), ("G2w", c_void_p), ("gG1w", c_void_p), ("gG1b", c_void_p), ("gG2w", c_void_p),
+                ("triples", c_void_p), ("B", c_int64), ("dup_counts", c_void_p),
+                ("margin", c_float), ("feat_margin", c_float),
+                ("flat_grad", c_void_p), ("n_params", c_int64),
+                ("workspace", c_void_p), ("workspace_bytes", c_int64),
+                ("loss_out", c_void_p), ("batch", c_void_p), ("diag_out", c_void_p), ("emb_out", ctypes.POINTER(c_void_p))]
+
+
+_SIGNATURES.update({
+    "ps_train_step_workspace": ([ctypes.POINTER(StepArgsC)], c_int64),
+    "ps_train_step": ([ctypes.POINTER(StepArgsC), c_void_p], c_int),
+    "ps_profile_enable": ([c_int], c_int),
+    "ps_profile_dump": ([c_char_p, c_int64], c_int64),
+})
+
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)
 
 
@@ -148,6 +181,32 @@ class Profiler:
 
 
 profiler = None  # set to a Profiler() to time every ABI call
+
+
+def native_profile(on: bool):
+    """Device timing of the launches inside ps_train_step (csrc/step.cu): enable / disable + reset."""
+    check(lib().ps_profile_enable(int(bool(on))))
+
+
+def native_profile_summary():
+    """{tag: {ms, launches, flops, bytes}} of the tagged launches since native_profile(True) (synchronises the device)."""
+    need = lib().ps_profile_dump(None, 0)
+    if need < 0:
+        raise NativeError("ps_profile_dump failed")
+    buf = ctypes.create_string_buffer(int(need) + 16)
+    n = lib().ps_profile_dump(buf, len(buf))
+    out = {}
+    for line in buf.value[: max(n, 0)].decode().splitlines():
+        tag, ms, launches, flops, nbytes = line.split()
+        out[tag] = {"ms": float(ms), "launches": int(launches), "flops": float(flops), "bytes": float(nbytes)}
+    return out
+
+
+def train_step(args: "StepArgsC", launches: int):
+    """ps_train_step on the current stream; `launches` = kernel launches it issues (bench.py's launch count)."""
+    global launch_count
+    launch_count += launches
+    check(lib().ps_train_step(ctypes.byref(args), c_void_p(torch.cuda.current_stream().cuda_stream)))
 
 
 class _Timed:

@@ -221,6 +221,51 @@ int ps_train_diagnostics(const float* feats, int64_t ld_feats, int d_feat, const
                          const float* emb, int64_t ld_emb, int d_emb, const int32_t* triples, float feat_margin,
                          float* out2, ps_stream_t stream);
 
+/* ---- the fused training step as ONE host call (PinSage.train_batch's three forwards + max_margin_loss + backward,
+ *      pinsage_training.py:184-190, on the shared frontier of the batch): forward of every layer of the plan, head,
+ *      loss, backward into flat_grad (zeroed by the call), optional diagnostics.  The frontier plan (ps_plan_layer /
+ *      ps_plan_transpose outputs per layer) and the parameters are passed by pointer; activations live in a caller-owned
+ *      workspace of ps_train_step_workspace(args) bytes.  No host synchronisation; ~45 launches on `stream`. ---- */
+#define PS_MAX_LAYERS 8
+#define PS_AGG_BWD_CHUNK 64
+typedef struct ps_layer_plan {
+    int64_t n, nz;              /* targets of the layer; rows of its input that get the Q transform */
+    const int32_t* self_rows;   /* [n]    row of each target in the layer input */
+    const int32_t* nbz;         /* [n,T]  row of each neighbour among the transformed rows */
+    const float* w;             /* [n,T]  importance weights */
+    const int32_t* zrows;       /* [nz]   gather index into the feature table (layer 0) or NULL */
+    const int32_t* seg_off;     /* [nz+1] backward transpose (ps_plan_transpose) */
+    const int32_t* pair_q;      /* [n*T] */
+    const int32_t* chunk_off;   /* [nz+1] */
+    const int32_t* chunk_row;   /* [n*T/64 + nz] */
+} ps_layer_plan;
+typedef struct ps_layer_params {
+    const float *Qw, *Qb, *Ww, *Wb; /* ConvLayer.Q / .W (pinsage_model.py:181-187): [dh,din], [dh], [do,din+dh], [do] */
+    float *gQw, *gQb, *gWw, *gWb;   /* their gradients (views of flat_grad) */
+} ps_layer_params;
+typedef struct ps_step_args {
+    int32_t n_layers, T, in_dim, hidden_dim, out_dim, reserved;
+    const float* feats; int64_t ld_feats;
+    ps_layer_plan layers[PS_MAX_LAYERS];
+    ps_layer_params params[PS_MAX_LAYERS];
+    const float *G1w, *G1b, *G2w; float *gG1w, *gG1b, *gG2w;
+    const int32_t* triples; int64_t B;   /* [B,3] rows of the top layer's output per (q, pos, neg) */
+    const int32_t* dup_counts;           /* [3, n_top] per-column occurrence counts (reference's duplicate factor) or NULL */
+    float margin, feat_margin;
+    float* flat_grad; int64_t n_params;
+    void* workspace; int64_t workspace_bytes;
+    float* loss_out;                     /* [1] */
+    const int64_t* batch; float* diag_out; /* optional diagnostics: batch int64 [B,3] node ids, diag_out [2] (ps_train_diagnostics) */
+    float** emb_out;                     /* optional HOST location that receives the device pointer of the [n_top, out_dim] embeddings */
+} ps_step_args;
+int64_t ps_train_step_workspace(const ps_step_args* args);
+int ps_train_step(const ps_step_args* args, ps_stream_t stream);
+/* Per-call device timing of the launches inside ps_train_step (bench.py's roofline leg): enable, run steps, dump
+ * "tag ms launches flops bytes" lines (synchronises the device).  ps_profile_dump returns the bytes written, or the
+ * size needed when `out` is NULL / too small. */
+int ps_profile_enable(int on);
+int64_t ps_profile_dump(char* out, int64_t cap);
+
 /* ---- K13: Adam step on a flat fp32 parameter buffer (torch.optim.Adam defaults:
  *      betas, eps, no weight decay, no amsgrad; pinsage_training.py:147,191).
  *      step is the 1-based step count used for bias correction. ---- */
