@@ -477,6 +477,8 @@ def run_ours(args, wl):
     trainer.batch_size = B
     trainer.online_sampling = args.sampling == "online"
     trainer.prep_workers = args.prep_workers
+    if args.steps_in_flight >= 0:
+        trainer.max_steps_in_flight = args.steps_in_flight
     ps_dist.attach(trainer, rank, world)
     nbhds_cpu = trainer.nbhds
 
@@ -758,6 +760,7 @@ def main():
     ap.add_argument("--setup-steps", type=int, default=8, help="extra untimed steps before the W warm-up steps (allocator steady state)")
     ap.add_argument("--exchange", action="store_true", help="infer mode: all-gather layer outputs instead of recomputing the closure")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--steps-in-flight", type=int, default=-1, help="override PinSage.max_steps_in_flight (0 = unlimited; development)")
     ap.add_argument("--no-extras", action="store_true", help="skip the `extra` sub-lines (strong scaling, online sampling, walker modes, cfg1 / cfg2, TF32 peak)")
     ap.add_argument("--tc-waves", type=int, default=0, help="override ps_gemm_tc_waves (development)")
     ap.add_argument("--gemm-reserve-sms", type=int, default=0, help="ps_gemm_tc_reserve_sms: SMs the persistent GEMMs leave free (development)")

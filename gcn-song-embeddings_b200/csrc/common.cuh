@@ -10,6 +10,8 @@
 #define PS_ERR_CUDA (-2)
 #define PS_ERR_GRAPH (-3)
 #define PS_ERR_UNSUPPORTED (-4)
+#define PS_ERR_NOSPACE (-5)
+#define PS_ERR_RANGE (-6)
 
 #define PS_LEAKY_SLOPE 0.01f
 

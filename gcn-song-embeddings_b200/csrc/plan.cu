@@ -117,6 +117,49 @@ __global__ void chunk_row_kernel(const int32_t* __restrict__ chunk_off, int64_t 
 
 inline unsigned blocks_for(int64_t n) { return static_cast<unsigned>(ps_ceil_div(n > 0 ? n : 1, 256)); }
 
+// ---- kernels of ps_prepare_plan
+__global__ void mark_ids64_kernel(const int64_t* __restrict__ ids, int64_t n, int64_t n_ids, int32_t* __restrict__ flag,
+                                  int32_t* __restrict__ bad) {
+    const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int64_t id = ids[i];
+    if (static_cast<uint64_t>(id) < static_cast<uint64_t>(n_ids)) flag[id] = 1;
+    else atomicAdd(bad, 1);
+}
+
+__global__ void positions64_kernel(const int32_t* __restrict__ pos, const int64_t* __restrict__ ids, int64_t n, int32_t* __restrict__ out) {
+    const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = pos[ids[i]];
+}
+
+// nb[i, t] = table_nodes[cur[i], t], w[i, t] = table_w[cur[i], t] for t < T   (NeighborTable.lookup)
+__global__ void lookup_kernel(const int64_t* __restrict__ cur, int64_t n, const int32_t* __restrict__ tab_nodes,
+                              const float* __restrict__ tab_w, int Tp, int T, int32_t* __restrict__ nb, float* __restrict__ w) {
+    const int64_t e = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (e >= n * T) return;
+    const int64_t i = e / T;
+    const int t = static_cast<int>(e - i * T);
+    const int64_t src = cur[i] * Tp + t;
+    nb[e] = __ldg(tab_nodes + src);
+    w[e] = __ldg(tab_w + src);
+}
+
+__global__ void narrow_ids_kernel(const int64_t* __restrict__ in, int64_t n, int32_t* __restrict__ out) {
+    const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = static_cast<int32_t>(in[i]);
+}
+
+struct PlanArena {
+    char* base; int64_t cap, off;
+    template <typename T> bool take(int64_t count, T** out, int64_t* off_out) {
+        const int64_t bytes = (count * static_cast<int64_t>(sizeof(T)) + 255) & ~static_cast<int64_t>(255);
+        *off_out = off;
+        *out = reinterpret_cast<T*>(base + off);
+        off += bytes;
+        return off <= cap;
+    }
+};
+
 }  // namespace
 
 extern "C" int ps_plan_layer(const int32_t* nb, int64_t n, int T, const int64_t* cur, int with_self, int64_t n_ids,
@@ -190,5 +233,133 @@ extern "C" int ps_plan_transpose(const int32_t* nbz, int64_t n_pairs, int64_t nz
         chunk_row_kernel<<<blocks_for(max_chunks), 256, 0, stream>>>(chunk_off, nz, max_chunks, chunk_row);
         PS_LAUNCH_CHECK();
     }
+    return PS_OK;
+}
+
+
+// The whole index-only preparation of a training batch in ONE host call (Engine.prepare composed it from ~25 calls):
+//   top      = sorted distinct node ids of batch [B,3]           (the shared frontier's top layer)
+//   triples  = position of every batch entry in `top`, counts = per-column occurrences (the duplicate-node factor)
+//   per layer l = L-1 .. 0 (relevant_nodes_per_layer_precomp, pinsage_model.py:156-168): neighbourhood lookup of the
+//   layer's targets, next frontier through the dense flag map, positions, and the backward transpose.
+// Sizes are only known on the device, so the call synchronises `stream` L+1 times (one 4-byte read each) and lays the
+// outputs out back to back in the caller's arena; `out` receives sizes and byte offsets.  Returns PS_ERR_NOSPACE (with
+// out->bytes_needed = a size that is certainly enough for the part reached) when the arena is too small: grow and retry.
+extern "C" int ps_prepare_plan(const int64_t* batch, int64_t B, const int32_t* tab_nodes, const float* tab_w, int64_t n_ids, int Tp,
+                               int T, int n_layers, int need_backward, void* arena_, int64_t arena_bytes, ps_plan_desc* out,
+                               ps_stream_t stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    PS_REQUIRE(batch && tab_nodes && tab_w && arena_ && out, "null pointer");
+    PS_REQUIRE(B > 0 && T > 0 && T <= Tp && n_layers >= 1 && n_layers <= PS_MAX_LAYERS, "bad shape (T must not exceed the table width)");
+    PS_REQUIRE(n_ids > 0 && n_ids < (1ll << 31), "bad id space");
+    memset(out, 0, sizeof(*out));
+    PlanArena ar{static_cast<char*>(arena_), arena_bytes, 0};
+    void* p = nullptr;
+    int rc = scratch(stream, 0, static_cast<size_t>(2 * (n_ids + 1) + 2) * sizeof(int32_t), &p);
+    if (rc != PS_OK) return rc;
+    int32_t* flag = static_cast<int32_t*>(p);
+    int32_t* pos = flag + (n_ids + 1);
+    int32_t* bad = pos + (n_ids + 1);
+    size_t scan_bytes = 0;
+    PS_CUDA_CHECK(cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, flag, pos, static_cast<int>(n_ids + 1), stream));
+    void* scan_tmp = nullptr;
+    rc = scratch(stream, 1, scan_bytes, &scan_tmp);
+    if (rc != PS_OK) return rc;
+    int32_t h_count[2] = {0, 0};
+#define PS_NOSPACE(need_more)                                                   \
+    do {                                                                        \
+        out->bytes_needed = ar.off + static_cast<int64_t>(need_more) + 4096;    \
+        return PS_ERR_NOSPACE;                                                  \
+    } while (0)
+
+    // ---- top = unique(batch), triples, counts
+    const int64_t nb3 = 3 * B;
+    PS_CUDA_CHECK(cudaMemsetAsync(flag, 0, static_cast<size_t>(2 * (n_ids + 1) + 2) * sizeof(int32_t), stream));
+    mark_ids64_kernel<<<blocks_for(nb3), 256, 0, stream>>>(batch, nb3, n_ids, flag, bad);
+    PS_LAUNCH_CHECK();
+    PS_CUDA_CHECK(cub::DeviceScan::ExclusiveSum(scan_tmp, scan_bytes, flag, pos, static_cast<int>(n_ids + 1), stream));
+    PS_CUDA_CHECK(cudaMemcpyAsync(&h_count[0], pos + n_ids, sizeof(int32_t), cudaMemcpyDeviceToHost, stream));
+    PS_CUDA_CHECK(cudaMemcpyAsync(&h_count[1], bad, sizeof(int32_t), cudaMemcpyDeviceToHost, stream));
+    PS_CUDA_CHECK(cudaStreamSynchronize(stream));
+    if (h_count[1] != 0) return ps_fail(PS_ERR_RANGE, "node id out of range");
+    const int64_t U = h_count[0];
+    out->U = U;
+    int64_t* top = nullptr; int32_t* triples = nullptr; int32_t* counts = nullptr;
+    bool ok = ar.take<int64_t>(U, &top, &out->off_top);
+    ok = ar.take<int32_t>(nb3, &triples, &out->off_triples) && ok;
+    ok = ar.take<int32_t>(3 * U, &counts, &out->off_counts) && ok;
+    if (!ok) PS_NOSPACE(0);
+    compact_kernel<<<blocks_for(n_ids), 256, 0, stream>>>(flag, pos, n_ids, top, nullptr);
+    PS_LAUNCH_CHECK();
+    positions64_kernel<<<blocks_for(nb3), 256, 0, stream>>>(pos, batch, nb3, triples);
+    PS_LAUNCH_CHECK();
+    rc = ps_count_triples(triples, B, U, counts, stream_);
+    if (rc != PS_OK) return rc;
+
+    // ---- layers, top down
+    const int64_t* cur = top;
+    int64_t n = U;
+    for (int l = n_layers - 1; l >= 0; --l) {
+        ps_plan_desc_layer& d = out->layers[l];
+        const bool with_self = l > 0;
+        const int64_t n_nb = n * T;
+        PS_REQUIRE(n_nb < (1ll << 31), "too many (target, slot) pairs in one layer");
+        int32_t* nb = nullptr; float* w = nullptr; int32_t* nbz = nullptr; int32_t* self_rows = nullptr;
+        int64_t off_nb_tmp = 0;
+        d.n = n;
+        d.off_nodes = reinterpret_cast<const char*>(cur) - ar.base;
+        ok = ar.take<float>(n_nb, &w, &d.off_w);
+        ok = ar.take<int32_t>(n_nb, &nbz, &d.off_nbz) && ok;
+        ok = ar.take<int32_t>(n, &self_rows, &d.off_self_rows) && ok;
+        if (!ok) PS_NOSPACE(n_nb * 16);
+        // raw neighbour ids: a temporary at the arena's current end (overwritten by what is carved next)
+        const int64_t save = ar.off;
+        ok = ar.take<int32_t>(n_nb, &nb, &off_nb_tmp);
+        if (!ok) PS_NOSPACE(n_nb * 12);
+        lookup_kernel<<<blocks_for(n_nb), 256, 0, stream>>>(cur, n, tab_nodes, tab_w, Tp, T, nb, w);
+        PS_LAUNCH_CHECK();
+        PS_CUDA_CHECK(cudaMemsetAsync(flag, 0, static_cast<size_t>(n_ids + 1) * sizeof(int32_t), stream));
+        mark_kernel<<<blocks_for(n_nb), 256, 0, stream>>>(nb, n_nb, cur, n, with_self ? 1 : 0, n_ids, flag);
+        PS_LAUNCH_CHECK();
+        PS_CUDA_CHECK(cub::DeviceScan::ExclusiveSum(scan_tmp, scan_bytes, flag, pos, static_cast<int>(n_ids + 1), stream));
+        inverse_kernel<<<blocks_for(n_nb), 256, 0, stream>>>(pos, nb, n_nb, cur, n, with_self ? 1 : 0, n_ids, nbz, self_rows);
+        PS_LAUNCH_CHECK();
+        if (!with_self) {
+            narrow_ids_kernel<<<blocks_for(n), 256, 0, stream>>>(cur, n, self_rows);  // layer 0 reads the feature table by node id
+            PS_LAUNCH_CHECK();
+        }
+        PS_CUDA_CHECK(cudaMemcpyAsync(&h_count[0], pos + n_ids, sizeof(int32_t), cudaMemcpyDeviceToHost, stream));
+        PS_CUDA_CHECK(cudaStreamSynchronize(stream));
+        const int64_t nz = h_count[0];
+        d.nz = nz;
+        ar.off = save;  // the raw ids are dead once nbz exists
+        int64_t* uniq64 = nullptr; int32_t* uniq32 = nullptr;
+        d.off_zrows = -1;
+        if (with_self) {
+            int64_t off_next = 0;
+            if (!ar.take<int64_t>(nz, &uniq64, &off_next)) PS_NOSPACE(nz * 64);
+        } else {
+            if (!ar.take<int32_t>(nz, &uniq32, &d.off_zrows)) PS_NOSPACE(nz * 64);
+        }
+        compact_kernel<<<blocks_for(n_ids), 256, 0, stream>>>(flag, pos, n_ids, uniq64, uniq32);
+        PS_LAUNCH_CHECK();
+        d.off_seg_off = d.off_pair_q = d.off_chunk_off = d.off_chunk_row = -1;
+        if (need_backward) {
+            const int64_t max_chunks = n_nb / PS_AGG_BWD_CHUNK + nz;
+            int32_t *pair_q = nullptr, *seg_off = nullptr, *chunk_off = nullptr, *chunk_row = nullptr;
+            ok = ar.take<int32_t>(n_nb, &pair_q, &d.off_pair_q);
+            ok = ar.take<int32_t>(nz + 1, &seg_off, &d.off_seg_off) && ok;
+            ok = ar.take<int32_t>(nz + 1, &chunk_off, &d.off_chunk_off) && ok;
+            ok = ar.take<int32_t>(max_chunks > 1 ? max_chunks : 1, &chunk_row, &d.off_chunk_row) && ok;
+            if (!ok) PS_NOSPACE(0);
+            rc = ps_plan_transpose(nbz, n_nb, nz, PS_AGG_BWD_CHUNK, pair_q, seg_off, chunk_off, chunk_row, max_chunks, stream_);
+            if (rc != PS_OK) return rc;
+        }
+        cur = uniq64;
+        n = nz;
+    }
+#undef PS_NOSPACE
+    out->bytes_used = ar.off;
+    out->bytes_needed = ar.off;
     return PS_OK;
 }

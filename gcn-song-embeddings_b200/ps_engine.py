@@ -141,6 +141,7 @@ class LayerPlan:
 class Plan:
     top: torch.Tensor            # int64 [n_top] sorted distinct nodes whose embeddings are produced
     layers: List[LayerPlan] = field(default_factory=list)
+    arena: Optional[torch.Tensor] = None  # ps_prepare_plan: the one device buffer every tensor above is a view of
 
 
 def _unique_inverse(ids: torch.Tensor, n_ids: int, scratch: dict):
@@ -161,6 +162,38 @@ def _unique_inverse(ids: torch.Tensor, n_ids: int, scratch: dict):
     uniq = flag.nonzero().squeeze(1)
     inv = (pos[idx] - 1).to(torch.int64)
     return uniq, inv
+
+
+def prepare_native(batch: torch.Tensor, n_layers: int, T: int, table: NeighborTable, need_backward: bool = True):
+    """(Plan, triples int32 [B,3], counts int32 [3,U]) of a batch int64 [B,3] on the device through ONE host call
+    (ps_prepare_plan, csrc/plan.cu): what torch.unique + build_plan + count_triples compose from ~25 calls."""
+    if T > table.Tp:
+        raise ValueError(f"T={T} exceeds the precomputed neighbourhood width {table.Tp}")
+    arena, base, d = nat.prepare_plan(batch, table.nodes, table.w, T, n_layers, need_backward)
+    B = batch.shape[0]
+
+    def view(off, count, dtype, shape=None):
+        if off < 0:
+            return None
+        t = arena[base + off: base + off + count * dtype.itemsize].view(dtype)
+        return t.view(shape) if shape is not None else t
+
+    U = int(d.U)
+    top = view(d.off_top, U, torch.int64)
+    plan = Plan(top=top, layers=[None] * n_layers, arena=arena)
+    for l in range(n_layers):
+        c = d.layers[l]
+        n, nz = int(c.n), int(c.nz)
+        max_chunks = max(1, n * T // nat.AGG_BWD_CHUNK + nz)
+        plan.layers[l] = LayerPlan(
+            n=n, nz=nz, self_rows=view(c.off_self_rows, n, torch.int32), nbz=view(c.off_nbz, n * T, torch.int32, (n, T)),
+            w=view(c.off_w, n * T, torch.float32, (n, T)), zrows=view(c.off_zrows, nz, torch.int32),
+            seg_off=view(c.off_seg_off, nz + 1, torch.int32), pair_q=view(c.off_pair_q, n * T, torch.int32),
+            chunk_off=view(c.off_chunk_off, nz + 1, torch.int32), chunk_row=view(c.off_chunk_row, max_chunks, torch.int32),
+            nodes=view(c.off_nodes, n, torch.int64))
+    triples = view(d.off_triples, 3 * B, torch.int32, (B, 3))
+    counts = view(d.off_counts, 3 * U, torch.int32, (3, U))
+    return plan, triples, counts
 
 
 def build_plan(top: torch.Tensor, n_layers: int, T: int, table: NeighborTable, need_backward: bool, check_ids: bool = True) -> Plan:
@@ -230,6 +263,8 @@ class Prepared:
     ready: object            # CUDA event recorded on the side stream
 
     def tensors(self):
+        if self.plan.arena is not None:  # one storage behind every view
+            return [self.batch, self.plan.arena]
         out = [self.batch, self.triples, self.counts, self.plan.top]
         for lp in self.plan.layers:
             out += [t for t in (lp.self_rows, lp.nbz, lp.w, lp.zrows, lp.seg_off, lp.pair_q, lp.chunk_off, lp.chunk_row, lp.nodes) if t is not None]
@@ -408,13 +443,18 @@ class Engine:
             B = batch.shape[0]
             if timing is not None:
                 side.synchronize(); t1 = time.perf_counter(); timing["sample"] += t1 - t0
-            top, inv = torch.unique(batch.reshape(-1), return_inverse=True)
-            if timing is not None:
-                t2 = time.perf_counter(); timing["unique"] += t2 - t1
-            triples = inv.view(B, 3).to(torch.int32).contiguous()
-            plan = build_plan(top, m.n_layers, m.T, NeighborTable.of(m.nbhds), need_backward=True, check_ids=check_ids)
-            counts = torch.empty((3, top.numel()), dtype=torch.int32, device="cuda")
-            nat.count_triples(triples, top.numel(), counts)
+            table = NeighborTable.of(m.nbhds)
+            if isinstance(table, NeighborTable) and table.nodes.is_cuda and os.environ.get("PS_PY_PREPARE") != "1":
+                plan, triples, counts = prepare_native(batch.contiguous(), m.n_layers, m.T, table)  # one host call
+                t2 = t1 if timing is not None else 0.0
+            else:  # online neighbourhoods (the walker runs per layer), or PS_PY_PREPARE=1: composed from Python
+                top, inv = torch.unique(batch.reshape(-1), return_inverse=True)
+                if timing is not None:
+                    t2 = time.perf_counter(); timing["unique"] += t2 - t1
+                triples = inv.view(B, 3).to(torch.int32).contiguous()
+                plan = build_plan(top, m.n_layers, m.T, table, need_backward=True, check_ids=check_ids)
+                counts = torch.empty((3, top.numel()), dtype=torch.int32, device="cuda")
+                nat.count_triples(triples, top.numel(), counts)
             ready = torch.cuda.Event()
             ready.record(side)
             if timing is not None:

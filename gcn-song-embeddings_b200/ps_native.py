@@ -97,7 +97,20 @@ class StepArgsC(ctypes.Structure):
                 ("loss_out", c_void_p), ("batch", c_void_p), ("diag_out", c_void_p), ("emb_out", ctypes.POINTER(c_void_p))]
 
 
+class PlanDescLayerC(ctypes.Structure):
+    _fields_ = [(k, c_int64) for k in ("n", "nz", "off_nodes", "off_self_rows", "off_nbz", "off_w", "off_zrows",
+                                       "off_seg_off", "off_pair_q", "off_chunk_off", "off_chunk_row")]
+
+
+class PlanDescC(ctypes.Structure):
+    """ps_plan_desc of include/pinsage_b200.h."""
+    _fields_ = [("U", c_int64), ("off_top", c_int64), ("off_triples", c_int64), ("off_counts", c_int64),
+                ("layers", PlanDescLayerC * PS_MAX_LAYERS), ("bytes_used", c_int64), ("bytes_needed", c_int64)]
+
+
 _SIGNATURES.update({
+    "ps_prepare_plan": ([c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_int, c_int, c_int, c_int, c_void_p, c_int64,
+                         ctypes.POINTER(PlanDescC), c_void_p], c_int),
     "ps_train_step_workspace": ([ctypes.POINTER(StepArgsC)], c_int64),
     "ps_train_step": ([ctypes.POINTER(StepArgsC), c_void_p], c_int),
     "ps_profile_enable": ([c_int], c_int),
@@ -200,6 +213,37 @@ def native_profile_summary():
         tag, ms, launches, flops, nbytes = line.split()
         out[tag] = {"ms": float(ms), "launches": int(launches), "flops": float(flops), "bytes": float(nbytes)}
     return out
+
+
+PS_ERR_NOSPACE, PS_ERR_RANGE = -5, -6
+_arena_hint = {}  # (B, T, n_layers, n_ids) -> bytes that were enough last time
+
+
+def prepare_plan(batch, table_nodes, table_w, T, n_layers, need_backward=True):
+    """ps_prepare_plan on the current stream: (arena uint8 tensor, PlanDescC).  The arena is sized from the previous call
+    with the same shape and grown on demand (the sizes of the frontiers are only known on the device)."""
+    global launch_count
+    _ensure_device()
+    B = batch.shape[0]
+    n_ids, Tp = table_nodes.shape
+    key = (B, T, n_layers, n_ids)
+    size = _arena_hint.get(key, max(1 << 20, 64 * 3 * B * (T + 1) * T))
+    desc = PlanDescC()
+    while True:
+        arena = torch.empty(size + 256, dtype=torch.uint8, device="cuda")
+        base = (arena.data_ptr() + 255) & ~255
+        launch_count += 6 + 14 * n_layers
+        rc = lib().ps_prepare_plan(_p(batch, torch.int64), B, _p(table_nodes, torch.int32), _p(table_w, torch.float32), n_ids, Tp,
+                                   int(T), int(n_layers), int(need_backward), c_void_p(base), size, ctypes.byref(desc),
+                                   c_void_p(torch.cuda.current_stream().cuda_stream))
+        if rc == PS_ERR_NOSPACE:
+            size = max(int(desc.bytes_needed), 2 * size)
+            continue
+        if rc == PS_ERR_RANGE:
+            raise IndexError("node id out of range")  # the reference raises IndexError on OOB ids too
+        check(rc)
+        _arena_hint[key] = max(_arena_hint.get(key, 0), int(desc.bytes_used * 1.25) + 4096)
+        return arena, base - arena.data_ptr(), desc
 
 
 def train_step(args: "StepArgsC", launches: int):

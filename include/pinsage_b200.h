@@ -266,6 +266,32 @@ int ps_train_step(const ps_step_args* args, ps_stream_t stream);
 int ps_profile_enable(int on);
 int64_t ps_profile_dump(char* out, int64_t cap);
 
+/* ---- the index-only preparation of a training batch in ONE host call (what PinSageModel.forward does before the
+ *      first layer: relevant_nodes_per_layer_precomp, pinsage_model.py:156-168, 246-252, on the distinct nodes of the
+ *      batch): top = sorted distinct ids of batch [B,3], triples / per-column counts, and per layer the neighbourhood
+ *      lookup in the [n_ids, Tp] table, the next frontier, positions and the backward transpose (ps_plan_layer /
+ *      ps_plan_transpose).  Outputs are laid out in the caller's device arena; `out` (HOST) receives sizes and byte
+ *      offsets (-1 = absent).  Synchronises `stream` n_layers + 1 times.  PS_ERR_NOSPACE (-5): arena too small,
+ *      out->bytes_needed says how much the part reached needs -- grow and call again.  PS_ERR_RANGE (-6): a batch id is
+ *      outside [0, n_ids) (the reference raises IndexError). ---- */
+typedef struct ps_plan_desc_layer {
+    int64_t n, nz;
+    int64_t off_nodes;      /* int64 [n]   node id of every target (sorted, distinct) */
+    int64_t off_self_rows;  /* int32 [n] */
+    int64_t off_nbz;        /* int32 [n,T] */
+    int64_t off_w;          /* float [n,T] */
+    int64_t off_zrows;      /* int32 [nz]  (layer 0 only) */
+    int64_t off_seg_off, off_pair_q, off_chunk_off, off_chunk_row; /* backward transpose (need_backward) */
+} ps_plan_desc_layer;
+typedef struct ps_plan_desc {
+    int64_t U;                                   /* distinct nodes of the batch */
+    int64_t off_top, off_triples, off_counts;    /* int64 [U], int32 [B,3], int32 [3,U] */
+    ps_plan_desc_layer layers[PS_MAX_LAYERS];
+    int64_t bytes_used, bytes_needed;
+} ps_plan_desc;
+int ps_prepare_plan(const int64_t* batch, int64_t B, const int32_t* table_nodes, const float* table_w, int64_t n_ids, int Tp,
+                    int T, int n_layers, int need_backward, void* arena, int64_t arena_bytes, ps_plan_desc* out, ps_stream_t stream);
+
 /* ---- K13: Adam step on a flat fp32 parameter buffer (torch.optim.Adam defaults:
  *      betas, eps, no weight decay, no amsgrad; pinsage_training.py:147,191).
  *      step is the 1-based step count used for bias correction. ---- */

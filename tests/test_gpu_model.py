@@ -428,3 +428,40 @@ def test_online_train_step_vs_oracle():
     assert_close(emb[triples[:, 2].long()], o_hn, RTOL, "hn")
     for k, p in model.named_parameters():
         assert_close(p.grad, o_grads[k], RTOL, k)
+
+
+@pytest.mark.parametrize("n_tracks,T,L,B", [(900, 5, 2, 64), (5000, 12, 3, 300), (300, 3, 1, 1), (20_000, 50, 2, 256)])
+def test_native_prepare_equals_composed_prepare(n_tracks, T, L, B, monkeypatch):
+    """ps_prepare_plan (the whole batch preparation in one host call) == the preparation composed from torch.unique +
+    build_plan + ps_count_triples: top, triples, counts and every tensor of every layer plan; out-of-range ids raise
+    IndexError like the reference's table indexing; a too-small arena grows transparently."""
+    import ps_native
+    from ps_engine import NeighborTable, prepare_native, build_plan
+    rng = np.random.RandomState(n_tracks + T)
+    nodes = torch.from_numpy(np.stack([rng.choice(n_tracks, size=T + 2, replace=False) for _ in range(n_tracks)]).astype(np.int64))
+    w = torch.from_numpy(rng.randint(1, 40, size=(n_tracks, T + 2)).astype(np.float64) / 500)
+    table = NeighborTable(w, nodes, device="cuda")
+    batch = torch.from_numpy(rng.randint(0, n_tracks, size=(B, 3)).astype(np.int64)).cuda()
+    ps_native._arena_hint.clear()
+    ps_native._arena_hint[(B, T, L, n_tracks)] = 4096   # far too small: exercises the grow-and-retry path
+    plan, triples, counts = prepare_native(batch, L, T, table)
+    top, inv = torch.unique(batch.reshape(-1), return_inverse=True)
+    want = build_plan(top, L, T, table, need_backward=True)
+    assert torch.equal(plan.top, top) and torch.equal(triples.long(), inv.view(B, 3))
+    wc = torch.empty((3, top.numel()), dtype=torch.int32, device="cuda")
+    ps_native.count_triples(inv.view(B, 3).to(torch.int32).contiguous(), top.numel(), wc)
+    assert torch.equal(counts, wc)
+    for a, b in zip(plan.layers, want.layers):
+        assert (a.n, a.nz) == (b.n, b.nz)
+        for name in ("self_rows", "nbz", "w", "zrows", "seg_off", "pair_q", "chunk_off", "nodes"):
+            x, y = getattr(a, name), getattr(b, name)
+            assert (x is None) == (y is None), name
+            if x is not None:
+                assert torch.equal(x.to(y.dtype), y), name
+        total = int(b.chunk_off[-1])
+        assert torch.equal(a.chunk_row[:total], b.chunk_row[:total])
+    bad = batch.clone(); bad[0, 1] = n_tracks
+    with pytest.raises(IndexError):
+        prepare_native(bad, L, T, table)
+    with pytest.raises(ValueError):
+        prepare_native(batch, L, T + 3, table)
