@@ -585,8 +585,11 @@ def run_ours(args, wl):
         e2e_step()
     torch.cuda.synchronize(); ps_dist.barrier()
     w0 = time.perf_counter()
+    e2e_each = []
     for _ in range(args.steps):
+        s0 = time.perf_counter()
         e2e_step()
+        e2e_each.append((time.perf_counter() - s0) * 1e3)
     torch.cuda.synchronize(); ps_dist.barrier()
     e2e_ms = ps_dist.max_over_ranks((time.perf_counter() - w0) * 1e3 / args.steps)
     e2e_value = 3 * B * world / (e2e_ms * 1e-3)
@@ -658,7 +661,8 @@ def run_ours(args, wl):
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic", "config": workload_config(args.workload, wl, world),
             "e2e": {"value": round(e2e_value, 1), "unit": UNIT, "ms_per_step": round(e2e_ms, 3),
-                    "h2d_bytes_per_step": B * 3 * 8, "d2h_bytes_per_step": 4},
+                    "h2d_bytes_per_step": B * 3 * 8, "d2h_bytes_per_step": 4,
+                    "ms_per_step_median": round(statistics.median(e2e_each), 3), "ms_per_step_max": round(max(e2e_each), 3)},
             "gpu_launches": launches, "clocks": clocks,
             "walk": {"metric": "walk_steps_per_sec", "value": round(walk_steps_per_s, 1), "unit": "steps/s",
                      "sources": N, "n_hops": 500, "alpha": 0.85, "T": 100, "ms": round(walk_ms, 3),

@@ -70,7 +70,12 @@ def _n_items(g):
 
 
 def _load_embeddings(ids, load_dir):
-    """Stack the per-track `<id>.pt` vectors (baselines.py:281-294)."""
+    """The embeddings of `ids` as one matrix (baselines.py:281-294): the single-tensor copy beside `load_dir` when it
+    is there and lists exactly these ids (pinsage_training.save_embedding_matrix), else the per-track `<id>.pt` files."""
+    from pinsage_training import load_embedding_matrix
+    emb = load_embedding_matrix(load_dir, ids)
+    if emb is not None:
+        return emb
     emb_list = [torch.load(os.path.join(load_dir, track_id + ".pt")) for track_id in tqdm(ids, desc="Loading embeddings")]
     return torch.stack(emb_list, dim=0)
 

@@ -26,6 +26,8 @@ def save_embedding(model, model_name, ids, save_dir):
         t0 = time.time()
         emb = model.embed(torch.arange(0, len(ids), dtype=torch.int64))
         emb_time = time.time() - t0
+        from pinsage_training import save_embedding_matrix
+        save_embedding_matrix(save_dir, ids, emb)  # one tensor beside the per-track files (fast path of EmbLoader)
         for i in range(emb.shape[0]):
             torch.save(emb[i, :].clone().detach().cpu(), os.path.join(save_dir, ids[i] + ".pt"))
     return emb_time

@@ -192,8 +192,15 @@ class PinSage():
         self.hn_min = 10
         self.hn_max = 100
 
-        self.nbhds = psm.precompute_neighborhoods_topt(self.g, self.n, self.n_hops, self.alpha,
-                                                       psm.DEF_T_PRECOMP, self.precomp_path)
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            # data parallel: every rank walks 1/G of the sources, one all-gather of the shards (ps_dist)
+            import ps_dist
+            self.nbhds = ps_dist.precompute_neighborhoods_sharded(self.g, self.n, self.n_hops, self.alpha,
+                                                                  psm.DEF_T_PRECOMP, self.precomp_path)
+        else:
+            self.nbhds = psm.precompute_neighborhoods_topt(self.g, self.n, self.n_hops, self.alpha,
+                                                           psm.DEF_T_PRECOMP, self.precomp_path)
         self.model = psm.PinSageModel(self.g, self.n, self.n_layers, self.dimensions,
                                       self.n_hops, self.alpha, self.T, self.nbhds)
 
@@ -209,7 +216,7 @@ class PinSage():
         self.b_per_e = 500
 
         self.embeddings = None
-        self.max_steps_in_flight = 1   # device queue depth in steps (None / 0 = unlimited)
+        self.max_steps_in_flight = 2   # device queue depth in steps (None / 0 = unlimited)
         self.prep_workers = 1          # host threads preparing batches ahead of the training thread (prefetch_async)
         self.online_sampling = False   # True: run the walker inside every step (reference's online relevant_nodes_per_layer)
         self.reference_compat = True   # duplicate-node gradient factor, hard-negative row quirk
@@ -302,11 +309,11 @@ class PinSage():
         prep = batch if hasattr(batch, "plan") else self.prefetch(batch)
         batch = prep.batch
         feats = self._feats()
-        # At most `max_steps_in_flight` steps queued on the device.  With an always-full training queue the batch
-        # preparation (a chain of small dependent kernels on another stream) only advances one kernel per GEMM boundary
-        # -- every SM holds a persistent GEMM CTA -- and a preparation can take 2-3 steps (measured: 7.2 -> 12-19 ms
-        # per step, bimodal).  Waiting for the previous step before enqueuing the next one leaves the device to the
-        # preparation stream at every step boundary and costs ~2 % when everything is on time.
+        # At most `max_steps_in_flight` steps queued on the device.  With an unbounded training queue the host runs far
+        # ahead, the caching allocator has to find room for several steps' buffers at once (cudaMalloc inside the loop:
+        # measured 6.57 ms/step with occasional 7.7 ms runs), and the batch preparation's kernels (another stream) queue
+        # behind more resident GEMM CTAs.  Two steps keep the device busy across the step boundary (6.50 ms/step against
+        # 6.69 ms with one) without either effect.
         done = getattr(self, "_steps_in_flight", None)
         if done is None:
             from collections import deque
@@ -409,31 +416,68 @@ class PinSage():
         os.replace(tmp, path)
 
 
-def save_embeddings(trainer, dataset, base_run_dir=BASE_RUN_DIR, override_run_name=None):
-    """Embed all tracks in 256-row batches and save one `<track_id>.pt` (1-D float32 [out])
-    per track, skipping existing files (pinsage_training.py:297-327)."""
+def _matrix_path(emb_dir):
+    """The single-tensor copy of an embedding directory lives BESIDE it (`<...>/emb` -> `<...>/emb.all.pt`): the
+    reference's loaders count the files inside the directory (eval.py:100-103), so nothing may be added there."""
+    return emb_dir.rstrip("/\\") + ".all.pt"
+
+
+def save_embedding_matrix(emb_dir, track_ids, emb):
+    """One torch.save of {"track_ids": [...], "emb": float32 [N, out]} beside `emb_dir` (atomic): the fast path of
+    load_embeddings / EmbLoader.  The reference's format is one small file per track (pinsage_training.py:297-327):
+    10^6 torch.save / torch.load calls at cfg3 scale, minutes of file-system work around a 0.04 s embedding pass."""
+    path = _matrix_path(emb_dir)
+    tmp = f"{path}.tmp{os.getpid()}"
+    torch.save({"track_ids": list(track_ids), "emb": emb.detach().to("cpu", torch.float32).contiguous()}, tmp)
+    os.replace(tmp, path)
+    return path
+
+
+def load_embedding_matrix(emb_dir, track_ids):
+    """float32 [N, out] from the single-tensor copy if it exists and lists exactly `track_ids`, else None."""
+    path = _matrix_path(emb_dir)
+    if not os.path.isfile(path):
+        return None
+    blob = torch.load(path)
+    if list(blob.get("track_ids", [])) != list(track_ids):
+        return None
+    return blob["emb"]
+
+
+def save_embeddings(trainer, dataset, base_run_dir=BASE_RUN_DIR, override_run_name=None, per_track=True):
+    """Embed all tracks and save them (pinsage_training.py:297-327): one `<track_id>.pt` (1-D float32 [out]) per
+    track under `<base>/<run>/emb/`, skipping existing files, as the reference does -- plus ONE tensor with all of them
+    beside that directory (save_embedding_matrix).  The embeddings come from a single layer-wise pass over the graph
+    (Engine.embed_range) instead of N/256 frontier batches.  per_track=False writes only the single tensor."""
     track_ids = list(dataset.tracks)
     n = len(track_ids)
-    bsize = 256
     run_name = override_run_name if override_run_name else trainer.run_name
     emb_dir = os.path.join(base_run_dir, run_name, "emb")
     os.makedirs(emb_dir, exist_ok=True)
+    trainer.model.eval()
+    with torch.no_grad():
+        emb = trainer.model.engine.embed_range(trainer._feats(), 0, n).cpu()
+    trainer.embeddings = emb
+    save_embedding_matrix(emb_dir, track_ids, emb)
+    if not per_track:
+        return
     pbar = tqdm(total=n, desc="Saving embeddings")
-    for i in range(0, n, bsize):
-        ids = torch.arange(i, min(i + bsize, n))
-        emb = trainer.embed(ids)
-        for id in ids:
-            save_path = os.path.join(emb_dir, track_ids[id] + ".pt")
-            if os.path.isfile(save_path):
-                continue
-            torch.save(emb[id - i, :].clone().detach(), save_path)
-        pbar.update(bsize)
+    for i in range(n):
+        save_path = os.path.join(emb_dir, track_ids[i] + ".pt")
+        if not os.path.isfile(save_path):
+            torch.save(emb[i, :].clone().detach(), save_path)
+        if i % 256 == 255:
+            pbar.update(256)
     pbar.close()
 
 
 def load_embeddings(trainer, dataset, base_run_dir=BASE_RUN_DIR):
-    """Stack the saved per-track embeddings (pinsage_training.py:330-339)."""
+    """The saved embeddings as one [N, out] tensor (pinsage_training.py:330-339): from the single-tensor copy when it is
+    there and current, else by stacking the per-track files like the reference."""
     emb_dir = os.path.join(base_run_dir, trainer.run_name, "emb")
+    emb = load_embedding_matrix(emb_dir, list(dataset.tracks))
+    if emb is not None:
+        return emb
     return torch.stack([torch.load(os.path.join(emb_dir, t + ".pt")) for t in dataset.tracks], dim=0)
 
 

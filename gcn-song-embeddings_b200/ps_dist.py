@@ -128,6 +128,56 @@ def all_gather_rows_(table: torch.Tensor, lo: int, hi: int, world_size: int):
     return table
 
 
+def precompute_neighborhoods_sharded(g, n_items, n_hops, alpha, T, path, rank: int = None, world_size: int = None, seed=None):
+    """Data-parallel form of precompute_neighborhoods_topt (pinsage_model.py:109-132): rank r walks the sources
+    [r N / G, (r+1) N / G) (independent sources: draws are keyed by (seed, source, step), so the table does not depend
+    on the sharding), then ONE all-gather of the [N/G, T] shards (int32 ids + float32 weights: 0.8 GB in total at
+    1 M items, T = 100) leaves the full device table on every rank.  Returns the reference's (weights float64 [N,T],
+    nodes int64 [N,T]) tuple with the engine-native device table attached; rank 0 writes `path` (atomically) when given.
+    A cached file of the right shape is loaded by every rank instead, like the reference does."""
+    import os
+    import pinsage_model as psm
+    import ps_native
+    from ps_engine import NeighborTable
+    from ps_graph import as_psgraph
+    rank = (dist.get_rank() if dist.is_initialized() else 0) if rank is None else rank
+    world_size = (dist.get_world_size() if dist.is_initialized() else 1) if world_size is None else world_size
+    if path is not None and os.path.isfile(path):
+        weights, nodes = torch.load(path)
+        if weights.shape[0] == n_items and weights.shape[1] == T:
+            return (weights, nodes)
+    if seed is None:
+        seed = psm._next_seed()
+    if world_size > 1:  # one key for everybody: rank 0's
+        s = torch.tensor([seed & 0x7FFFFFFFFFFFFFFF], dtype=torch.int64, device="cuda" if dist.get_backend() == "nccl" else "cpu")
+        dist.broadcast(s, src=0)
+        seed = int(s[0])
+    lo, hi = shard_range(n_items, rank, world_size)
+    pg = as_psgraph(g, n_items)
+    out = ps_native.walk_topt(pg.device(), torch.arange(lo, hi, device="cuda"), n_hops, alpha, T, seed, want_i64=False, want_i32=True)
+    table = NeighborTable.__new__(NeighborTable)
+    table.n, table.Tp, table.scratch = n_items, T, {}
+    if world_size > 1:
+        table.nodes = torch.empty((n_items, T), dtype=torch.int32, device="cuda")
+        table.w = torch.empty((n_items, T), dtype=torch.float32, device="cuda")
+        table.nodes[lo:hi], table.w[lo:hi] = out["nodes_i32"], out["weights_f32"]
+        all_gather_rows_(table.nodes, lo, hi, world_size)   # the single exchange step of the precompute
+        all_gather_rows_(table.w, lo, hi, world_size)
+    else:
+        table.nodes, table.w = out["nodes_i32"], out["weights_f32"]
+    # boundary format of the reference: float64 weights = count / n_hops.  Only the float32 table was exchanged; the
+    # integer count is recovered from it exactly (n_hops <= 16384) and divided again in float64
+    counts = torch.round(table.w.double() * n_hops).cpu()
+    # IEEE division element by element (a framework scalar division may multiply by the reciprocal instead)
+    weights, nodes = counts / torch.full_like(counts, float(n_hops)), table.nodes.to(torch.int64).cpu()
+    if path is not None and rank == 0:
+        tmp = f"{path}.tmp{os.getpid()}"
+        torch.save((weights, nodes), tmp)
+        os.replace(tmp, path)
+    weights._ps_table = table
+    return (weights, nodes)
+
+
 def embed_shard(trainer, rank: int = None, world_size: int = None, chunk: int = 1 << 18, stats=None, exchange: bool = False):
     """Node-range sharded full-graph inference (BASELINE.json configs[3]): this rank's rows
     [lo, hi) of the embedding matrix, float32 on the device.  Graph, features and neighbourhood table are replicated.

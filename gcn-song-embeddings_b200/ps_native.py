@@ -230,6 +230,7 @@ def prepare_plan(batch, table_nodes, table_w, T, n_layers, need_backward=True):
     size = _arena_hint.get(key, max(1 << 20, 64 * 3 * B * (T + 1) * T))
     desc = PlanDescC()
     while True:
+        size = ((size + 256 + (1 << 24) - 1) >> 24 << 24) - 256  # 16 MB buckets: the caching allocator reuses the same blocks
         arena = torch.empty(size + 256, dtype=torch.uint8, device="cuda")
         base = (arena.data_ptr() + 255) & ~255
         launch_count += 6 + 14 * n_layers

@@ -61,6 +61,12 @@ def _worker(rank, world, port, out):
         table[lo:hi] = want[lo:hi]
         ps_dist.all_gather_rows_(table, lo, hi, world)
         assert torch.equal(table, want), n
+        # the neighbourhood-table exchange of the sharded precompute: int32 ids
+        ids = torch.full((n, 5), -1, dtype=torch.int32)
+        want_ids = torch.arange(n * 5, dtype=torch.int32).view(n, 5)
+        ids[lo:hi] = want_ids[lo:hi]
+        ps_dist.all_gather_rows_(ids, lo, hi, world)
+        assert torch.equal(ids, want_ids), n
     # identically seeded replicas still draw DIFFERENT batches once attached (ps_dist.seed_rank_streams)
     import pinsage_training as pst
     torch.manual_seed(1234)                      # the mistake a data-parallel script makes on every rank

@@ -61,6 +61,23 @@ def test_dashboard_train_eval_flow(tmp_path, monkeypatch):
     # the cached kNN lists are the reference's 5-tuple
     knn_w, knn_n, *_times = torch.load(tmp_path / "eval_cache" / "knn" / "PinsageBase.pt")
     assert knn_n.shape == (400, 50)
+    # embedding persistence: the reference's per-track files AND one tensor beside the directory (the fast path);
+    # both readers return the same matrix, which equals the frontier-batched PinSage.embed the reference saves
+    from baselines import _load_embeddings
+    dataset = dashboard.SpotifyGraph(d, os.path.join(d, "features_openl3"))
+    ids = list(dataset.tracks)
+    assert os.path.isfile(str(emb_dir) + ".all.pt") and len(os.listdir(emb_dir)) == 400  # nothing extra INSIDE emb/
+    fast = pt.load_embeddings(trainer, dataset)
+    assert torch.equal(fast, _load_embeddings(ids, str(emb_dir)))
+    os.rename(str(emb_dir) + ".all.pt", str(emb_dir) + ".all.moved")
+    slow = pt.load_embeddings(trainer, dataset)            # per-track files, stacked like the reference
+    assert torch.equal(fast, slow) and torch.equal(slow, _load_embeddings(ids, str(emb_dir)))
+    want = trainer.embed(torch.arange(400))
+    assert torch.allclose(fast, want, rtol=1e-5, atol=1e-6)
+    os.rename(str(emb_dir) + ".all.moved", str(emb_dir) + ".all.pt")
+    assert pt.load_embedding_matrix(str(emb_dir), ids[::-1]) is None   # a stale / different id list is not trusted
+    pt.save_embeddings(trainer, dataset, per_track=False, override_run_name="t2")
+    assert os.listdir(tmp_path / "runs" / "t2" / "emb") == [] and os.path.isfile(tmp_path / "runs" / "t2" / "emb.all.pt")
 
 
 def test_eval_parity_with_reference_run(golden, tmp_path, monkeypatch):

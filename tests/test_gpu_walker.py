@@ -165,3 +165,31 @@ def test_module_level_api(golden):
     assert torch.equal(tw, w)
     weights, nodes = psm.precompute_neighborhoods_topt(pg, nt, 500, 0.85, 100, None, seed=4)
     assert weights.shape == (nt, 100) and weights.dtype == torch.float64 and nodes.dtype == torch.int64
+
+
+def test_sharded_precompute_equals_single_pass(tmp_path):
+    """ps_dist.precompute_neighborhoods_sharded (rank r walks its node range, one all-gather): the shards of a 3-rank
+    split, walked separately, tile exactly the table of a single pass with the same key (draws are keyed by
+    (seed, source, step), never by launch shape), and the world-size-1 call returns the reference's tuple format
+    (pinsage_model.py:109-132) equal to precompute_neighborhoods_topt's."""
+    import ps_dist
+    import ps_native
+    import ps_synth
+    import pinsage_model as psm
+    n_tracks = 5000
+    g = ps_synth.make_graph(n_tracks, 700, 60_000, seed=21)
+    w1, n1 = psm.precompute_neighborhoods_topt(g, n_tracks, 300, 0.85, 40, None, seed=77)
+    path = str(tmp_path / "nb.pt")
+    w2, n2 = ps_dist.precompute_neighborhoods_sharded(g, n_tracks, 300, 0.85, 40, path, rank=0, world_size=1, seed=77)
+    assert w2.dtype == torch.float64 and n2.dtype == torch.int64 and torch.equal(w1, w2) and torch.equal(n1, n2)
+    assert torch.equal(w2._ps_table.nodes.cpu().long(), n1)
+    lw, ln = torch.load(path)
+    assert torch.equal(lw, w1) and torch.equal(ln, n1)
+    w3, _ = ps_dist.precompute_neighborhoods_sharded(g, n_tracks, 300, 0.85, 40, path, rank=0, world_size=1, seed=5)  # cache hit
+    assert torch.equal(w3, w1)
+    parts = []
+    for r in range(3):
+        lo, hi = ps_dist.shard_range(n_tracks, r, 3)
+        parts.append(ps_native.walk_topt(g.device(), torch.arange(lo, hi), 300, 0.85, 40, 77, want_i64=True))
+    assert torch.equal(torch.cat([p["nodes"] for p in parts]).cpu(), n1)
+    assert torch.equal(torch.cat([p["weights"] for p in parts]).cpu(), w1)
