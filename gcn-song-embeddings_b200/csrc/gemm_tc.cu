@@ -33,6 +33,8 @@ constexpr int kProducerThreads = 256;
 constexpr int kThreads = 640;
 constexpr uint32_t kHiMask = 0xFFFFE000u;  // keep sign, exponent and the 10 tf32 mantissa bits
 constexpr int kEpiStride = 20;             // floats per staged row: 16 columns + 4 pad (conflict-free STS.128)
+constexpr int kPrefetchKb = 6;             // weight-gradient producers: L2 prefetch distance in k-blocks
+__device__ int g_tc_prefetch = 1;          // ps_gemm_tc_prefetch (development switch for the A/B comparison)
 
 struct TcArgs {
     const float* P; int64_t ldp; const int32_t* p_rows;
@@ -45,6 +47,7 @@ struct TcArgs {
     int64_t mt, nt, zs;  // work grid: M tiles x N tiles x K splits
     const uint8_t* bpack;  // BPACK kernels: hi/lo images of the Q operand, one [2][BN x 128 B] block per (n-tile, k-block)
     uint32_t* mask; int64_t ldm;  // optional sign mask of the activation, one bit per output element (ldm in 32-bit words)
+    unsigned long long* dbg;  // development: per-CTA cycle counters of the role waits (ps_gemm_tc_trace), nullptr = off
     float* p_colsum;  // weight-gradient kernels (MN-major x MN-major): p_colsum[i] += sum_r P(i, r) -- the bias gradient, from the
                       // elements the producers already hold for the hi/lo split (replaces a separate pass over P)
 };
@@ -72,6 +75,12 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         if (clock64() - t0 > 2000000000ll) __trap();
     }
 }
+__device__ __forceinline__ void mbar_wait_timed(uint32_t bar, uint32_t parity, unsigned long long* dbg, long long& acc) {
+    if (dbg == nullptr) { mbar_wait(bar, parity); return; }
+    const long long t0 = clock64();
+    mbar_wait(bar, parity);
+    acc += clock64() - t0;
+}
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
@@ -79,6 +88,11 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t byt
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+// the same, delivered to the same shared-memory offset of every CTA in `mask` (each one's mbarrier at that offset gets the bytes)
+__device__ __forceinline__ void bulk_g2s_multicast(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar, uint16_t mask) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar), "h"(mask) : "memory");
 }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
@@ -101,6 +115,10 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_c, uint64_t adesc, uint6
 }
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// arrive on the mbarrier at this offset in every CTA of `mask` once the MMAs issued so far have completed
+__device__ __forceinline__ void umma_commit_multicast(uint32_t bar, uint16_t mask) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"(mask) : "memory");
 }
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 "
@@ -273,6 +291,7 @@ template <typename OpA, typename OpB>
 struct LoadCursor {
     OpA a; OpB b;
     int64_t w; int kb; int nkb; int64_t k0; bool valid;
+    int64_t m0, n0;  // origin of the cursor's work item (L2 prefetch addresses)
 };
 
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint32_t src_bytes) {
@@ -288,16 +307,19 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 // BPACK: the Q operand (a weight matrix) was split into hi/lo and laid out as K-major SWIZZLE_128B tile images by
 // pack_b_kernel; one thread streams the image of every k-block into the stage with ONE bulk copy, and the eight
 // producer warps only move the activation operand, double-buffered in registers across k-blocks and tiles.
-template <bool PK, bool QK, int BN, bool BPACK, int MASK>  // MASK: 0 none, 1 = write sign bits (act 1), 2 = apply them (act 2)
+template <bool PK, bool QK, int BN, bool BPACK, int MASK, int CL>  // MASK: 0 none, 1 = write sign bits (act 1), 2 = apply them (act 2); CL: CTAs per cluster
 __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(TcArgs a) {
     static_assert(!BPACK || (PK && QK), "packed-B kernels take a K-major P and lay Q out K-major");
+    static_assert(CL == 1 || (BPACK && CL == 2), "clusters: packed-B kernels, pairs");
     constexpr int STAGES = BN == 256 ? 2 : 3;
     constexpr int HALF = BN / 2;            // columns owned by one epilogue thread
     constexpr int CHUNK_KB = 2;             // k-blocks accumulated in TMEM before the fp32 register drain
     constexpr uint32_t A_BYTES = BM * 128, B_BYTES = BN * 128;
     constexpr uint32_t STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+    // aligned by pointer arithmetic on the __shared__ array (not through an integer cast), so the compiler keeps the
+    // shared address space and emits LDS / STS instead of generic loads / stores
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
     float* ss_buf = reinterpret_cast<float*>(tmem_slot + 4);  // [2 parities][2 halves][128] partial sums of squares (l2norm)
@@ -307,16 +329,35 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(TcArgs a) {
     const uint32_t tfull0 = smem_u32(bars + 2 * STAGES), tempty0 = smem_u32(bars + 2 * STAGES + 2);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int64_t total_work = a.mt * a.nt * a.zs;
+    // CL == 2: two CTAs of a cluster work on vertically adjacent tiles (m, m + 1) of the SAME n-tile in lock step; each
+    // streams HALF of the packed weight image of a k-block and multicasts it into both CTAs' stages, so a weight byte
+    // crosses L2 -> SM once per tile PAIR.  (Measured before: these kernels move ~7 TB/s of L2 traffic, most of it the
+    // weight images re-streamed for every 128-row tile, and the tensor pipe idles 55-70 % of the time behind it.)
+    uint32_t cta_rank = 0;
+    if (CL > 1) asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(cta_rank));
+    const int64_t w_first = CL > 1 ? blockIdx.x / CL : blockIdx.x;
+    const int64_t w_step = CL > 1 ? gridDim.x / CL : gridDim.x;
+    const int64_t total_work = CL > 1 ? ((a.mt + CL - 1) / CL) * a.nt : a.mt * a.nt * a.zs;
+    auto decode = [&](int64_t w) -> Work {
+        if (CL > 1) {  // n-tile fastest, then tile pairs; no split-K on this path; a pair's second tile may lie beyond M
+            const int64_t n_idx = w % a.nt, mp = w / a.nt;
+            return {(mp * CL + cta_rank) * BM, n_idx * static_cast<int64_t>(BN), 0, static_cast<int>((a.K + BK - 1) / BK)};
+        }
+        return decode_work(a, w, BN);
+    };
 
     if (tid == 0) {
-        for (int s = 0; s < STAGES; ++s) { mbar_init(full0 + 8 * s, kProducerThreads + (BPACK ? 1 : 0)); mbar_init(empty0 + 8 * s, 1); }
+        for (int s = 0; s < STAGES; ++s) { mbar_init(full0 + 8 * s, kProducerThreads + (BPACK ? 1 : 0)); mbar_init(empty0 + 8 * s, CL); }  // a stage is free when every CTA of the cluster has read it
         for (int b = 0; b < 2; ++b) { mbar_init(tfull0 + 8 * b, 1); mbar_init(tempty0 + 8 * b, 8); }
         fence_barrier_init();
     }
     if (warp == 16) tmem_alloc<2 * BN>(smem_u32(tmem_slot));
     tc_fence_before();
     __syncthreads();
+    if (CL > 1) {  // the peer's barriers exist before anything is sent to them
+        asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+        asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+    }
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
@@ -331,16 +372,18 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(TcArgs a) {
             constexpr uint32_t A_LAY = PK ? 2u : 1u, B_LAY = QK ? 2u : 1u;
             int stage = 0; uint32_t phase = 0;
             uint32_t gc = 0;  // chunks issued so far (selects the TMEM buffer and its barrier parity)
-            for (int64_t w = blockIdx.x; w < total_work; w += gridDim.x) {
-                const Work wk = decode_work(a, w, BN);
+            long long d_full = 0, d_tempty = 0;
+            const long long d_t0 = clock64();
+            for (int64_t w = w_first; w < total_work; w += w_step) {
+                const Work wk = decode(w);
                 int kb = 0;
                 while (kb < wk.num_kb) {
                     const uint32_t buf = gc & 1;
-                    mbar_wait(tempty0 + 8 * buf, ((gc >> 1) & 1) ^ 1);  // the drain of this buffer's previous chunk is done
+                    mbar_wait_timed(tempty0 + 8 * buf, ((gc >> 1) & 1) ^ 1, a.dbg, d_tempty);  // the drain of this buffer's previous chunk is done
                     tc_fence_after();
                     const uint32_t tacc = tmem_base + buf * BN;
                     for (int q = 0; q < CHUNK_KB && kb < wk.num_kb; ++q, ++kb) {
-                        mbar_wait(full0 + 8 * stage, phase);
+                        mbar_wait_timed(full0 + 8 * stage, phase, a.dbg, d_full);
                         tc_fence_after();
                         const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
                         const uint32_t a_hi = sa, a_lo = sa + A_BYTES, b_hi = sa + 2 * A_BYTES, b_lo = b_hi + B_BYTES;
@@ -352,28 +395,37 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(TcArgs a) {
                             umma_tf32(tacc, dah, dbl, idesc, 1u);
                             umma_tf32(tacc, dah, dbh, idesc, 1u);
                         }
-                        umma_commit(empty0 + 8 * stage);  // frees the smem stage once these MMAs have read it
+                        if (CL > 1) umma_commit_multicast(empty0 + 8 * stage, static_cast<uint16_t>((1u << CL) - 1));  // ... in every CTA of the cluster
+                        else umma_commit(empty0 + 8 * stage);  // frees the smem stage once these MMAs have read it
                         if (++stage == STAGES) { stage = 0; phase ^= 1; }
                     }
                     umma_commit(tfull0 + 8 * buf);  // publishes the chunk to the accumulate warps
                     ++gc;
                 }
             }
+            if (a.dbg) { a.dbg[blockIdx.x * 8 + 0] = clock64() - d_t0; a.dbg[blockIdx.x * 8 + 1] = d_full; a.dbg[blockIdx.x * 8 + 2] = d_tempty; }
         }
         // ------------------------------------------------ packed-B stream (one lane of warp 17)
         if (BPACK && warp == 17 && lane == 0) {
             const int64_t nkb = (a.K + BK - 1) / BK;
             int stage = 0; uint32_t phase = 0;
-            for (int64_t w = blockIdx.x; w < total_work; w += gridDim.x) {
-                const Work wk = decode_work(a, w, BN);
+            long long d_empty = 0;
+            for (int64_t w = w_first; w < total_work; w += w_step) {
+                const Work wk = decode(w);
                 const uint8_t* src = a.bpack + ((wk.n0 / BN) * nkb + wk.kb_begin) * static_cast<int64_t>(2 * B_BYTES);
                 for (int kb = 0; kb < wk.num_kb; ++kb, src += 2 * B_BYTES) {
-                    mbar_wait(empty0 + 8 * stage, phase ^ 1);
+                    mbar_wait_timed(empty0 + 8 * stage, phase ^ 1, a.dbg, d_empty);
                     mbar_arrive_expect_tx(full0 + 8 * stage, 2 * B_BYTES);
-                    bulk_g2s(smem_u32(smem + stage * STAGE_BYTES + 2 * A_BYTES), src, 2 * B_BYTES, full0 + 8 * stage);
+                    if (CL > 1) {  // this CTA's half of the image ([hi | lo]: rank 0 sends hi, rank 1 lo), into both CTAs
+                        bulk_g2s_multicast(smem_u32(smem + stage * STAGE_BYTES + 2 * A_BYTES + cta_rank * B_BYTES), src + cta_rank * B_BYTES, B_BYTES,
+                                           full0 + 8 * stage, static_cast<uint16_t>((1u << CL) - 1));
+                    } else {
+                        bulk_g2s(smem_u32(smem + stage * STAGE_BYTES + 2 * A_BYTES), src, 2 * B_BYTES, full0 + 8 * stage);
+                    }
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
             }
+            if (a.dbg) a.dbg[blockIdx.x * 8 + 3] = d_empty;
         }
     } else if (warp >= 8 && BPACK) {
         asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
@@ -382,9 +434,9 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(TcArgs a) {
         using OpA = Operand<true, BM, true>;
         constexpr int NJ = OpA::NJ;
         OpA op;                       // the LOAD cursor: one k-block ahead of the stores, across tile boundaries
-        int64_t lw = blockIdx.x;
+        int64_t lw = w_first;
         int lkb = 0;
-        Work lwk = decode_work(a, lw < total_work ? lw : 0, BN);
+        Work lwk = decode(lw < total_work ? lw : 0);
         float4 cur[NJ], nxt[NJ];
         if (lw < total_work) {
             op.init(a.P, a.ldp, a.p_rows, lwk.m0, a.M, t);
@@ -392,18 +444,32 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(TcArgs a) {
         }
         const uint32_t off0 = op.off0;  // shared-memory offsets depend on the thread only, not on the tile
         int stage = 0; uint32_t phase = 0;
-        for (int64_t w = blockIdx.x; w < total_work; w += gridDim.x) {
-            const Work wk = decode_work(a, w, BN);
+        long long d_pempty = 0;
+        for (int64_t w = w_first; w < total_work; w += w_step) {
+            const Work wk = decode(w);
+            // L2 prefetch of the NEXT work item's activation rows (one 128-byte line per row and k-block).  The register
+            // double buffer keeps one k-block (16 KB per SM) in flight, which at HBM latency caps the operand stream near
+            // 2 TB/s chip-wide (the kernel's top stall was long-scoreboard in the producers); a whole tile ahead the lines
+            // arrive in L2 while the current tile is multiplied, and the loads below pay an L2 hit instead.
+            if (g_tc_prefetch && w + w_step < total_work) {
+                const Work nwk = decode(w + w_step);
+                int64_t i = nwk.m0 + (t & (BM - 1));
+                if (i >= a.M) i = a.M - 1;
+                const int64_t row = a.p_rows ? static_cast<int64_t>(__ldg(a.p_rows + i)) : i;
+                const float* src = a.P + row * a.ldp + static_cast<int64_t>(nwk.kb_begin) * BK;
+                for (int j = t >> 7; j < nwk.num_kb; j += kProducerThreads / BM)
+                    if (static_cast<int64_t>(nwk.kb_begin + j) * BK < a.K) asm volatile("prefetch.global.L2 [%0];" ::"l"(src + j * BK));
+            }
             for (int kb = 0; kb < wk.num_kb; ++kb) {
                 // advance the load cursor and issue the next k-block's loads before waiting for the stage
                 bool have_next = true;
                 if (++lkb == lwk.num_kb) {
-                    lw += gridDim.x; lkb = 0;
+                    lw += w_step; lkb = 0;
                     have_next = lw < total_work;
-                    if (have_next) { lwk = decode_work(a, lw, BN); op.init(a.P, a.ldp, a.p_rows, lwk.m0, a.M, t); }
+                    if (have_next) { lwk = decode(lw); op.init(a.P, a.ldp, a.p_rows, lwk.m0, a.M, t); }
                 }
                 if (have_next) op.template load<0, NJ>(nxt, static_cast<int64_t>(lwk.kb_begin + lkb) * BK, a.K);
-                mbar_wait(empty0 + 8 * stage, phase ^ 1);
+                mbar_wait_timed(empty0 + 8 * stage, phase ^ 1, t == 0 ? a.dbg : nullptr, d_pempty);
                 uint8_t* st = smem + stage * STAGE_BYTES;
 #pragma unroll
                 for (int j = 0; j < NJ; ++j) split_store(st, st + A_BYTES, off0 + j * OpA::kStep, cur[j]);
@@ -414,6 +480,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(TcArgs a) {
                 for (int j = 0; j < NJ; ++j) cur[j] = nxt[j];
             }
         }
+        if (a.dbg && t == 0) a.dbg[blockIdx.x * 8 + 4] = d_pempty;
     } else if (warp >= 8 && !PK && !QK) {
         asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
         // ------------------------------------------------ producers, MN-major x MN-major (weight gradients)
@@ -426,12 +493,13 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(TcArgs a) {
         using OpA = Operand<false, BM, true>;
         using OpB = Operand<false, BN, false>;
         LoadCursor<OpA, OpB> lc;
-        lc.w = blockIdx.x; lc.kb = 0;
+        lc.w = w_first; lc.kb = 0;
         lc.valid = lc.w < total_work;
         {
-            const Work wk = decode_work(a, lc.valid ? lc.w : 0, BN);
+            const Work wk = decode(lc.valid ? lc.w : 0);
             lc.nkb = wk.num_kb;
             lc.k0 = static_cast<int64_t>(wk.kb_begin) * BK;
+            lc.m0 = wk.m0; lc.n0 = wk.n0;
             lc.a.init(a.P, a.ldp, a.p_rows, wk.m0, a.M, t);
             lc.b.init(a.Q, a.ldq, a.q_rows, wk.n0, a.N, t);
         }
@@ -457,12 +525,13 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(TcArgs a) {
         };
         auto advance = [&]() {
             if (++lc.kb == lc.nkb) {
-                lc.w += gridDim.x; lc.kb = 0;
+                lc.w += w_step; lc.kb = 0;
                 lc.valid = lc.w < total_work;
                 if (lc.valid) {
-                    const Work wk = decode_work(a, lc.w, BN);
+                    const Work wk = decode(lc.w);
                     lc.nkb = wk.num_kb;
                     lc.k0 = static_cast<int64_t>(wk.kb_begin) * BK;
+                    lc.m0 = wk.m0; lc.n0 = wk.n0;
                     lc.a.init(a.P, a.ldp, a.p_rows, wk.m0, a.M, t);
                     lc.b.init(a.Q, a.ldq, a.q_rows, wk.n0, a.N, t);
                 }
@@ -476,8 +545,8 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(TcArgs a) {
             advance();
         }
         float4 csum = make_float4(0.f, 0.f, 0.f, 0.f);  // this thread's 4 P columns summed over the work item's k range
-        for (int64_t w = blockIdx.x; w < total_work; w += gridDim.x) {
-            const Work wk = decode_work(a, w, BN);
+        for (int64_t w = w_first; w < total_work; w += w_step) {
+            const Work wk = decode(w);
             for (int kb = 0; kb < wk.num_kb; ++kb) {
                 // split pass of the current k-block: its copies were issued one iteration ago
                 cp_async_wait_all();
@@ -506,6 +575,15 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(TcArgs a) {
                 if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 // copies of the next k-block into the stage that follows (free once the MMAs that read it are done)
                 if (lc.valid) {
+                    if (g_tc_prefetch) {  // L2 prefetch kPrefetchKb k-blocks ahead of the copies: 32 k-rows x (BM + BN) floats
+                        const int64_t kp = lc.k0 + static_cast<int64_t>(kPrefetchKb) * BK + (t >> 3);
+                        if (kp < a.K && lc.kb + kPrefetchKb < lc.nkb) {
+                            const int line = t & 7;  // a Q row of BN floats = BN / 32 lines, a P row of BM floats = BM / 32 lines
+                            const int64_t qrow = lc.b.rows ? static_cast<int64_t>(__ldg(lc.b.rows + kp)) : kp;
+                            if (line < BN / 32 && lc.n0 + line * 32 < a.N) asm volatile("prefetch.global.L2 [%0];" ::"l"(a.Q + qrow * a.ldq + lc.n0 + line * 32));
+                            if (line < BM / 32 && lc.m0 + line * 32 < a.M) asm volatile("prefetch.global.L2 [%0];" ::"l"(a.P + kp * a.ldp + lc.m0 + line * 32));
+                        }
+                    }
                     mbar_wait(empty0 + 8 * stage, phase ^ 1);
                     issue(stage);
                     advance();
@@ -528,8 +606,8 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(TcArgs a) {
         using OpB = Operand<QK, BN, false>;
         constexpr int HB = OpB::NJ / 2;
         int stage = 0; uint32_t phase = 0;
-        for (int64_t w = blockIdx.x; w < total_work; w += gridDim.x) {
-            const Work wk = decode_work(a, w, BN);
+        for (int64_t w = w_first; w < total_work; w += w_step) {
+            const Work wk = decode(w);
             OpA opa;
             OpB opb;
             opa.init(a.P, a.ldp, a.p_rows, wk.m0, a.M, t);
@@ -561,14 +639,27 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(TcArgs a) {
         const uint32_t tlane = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + half * HALF;
         uint32_t gc = 0, tile_par = 0;
         float acc[HALF];
-        for (int64_t w = blockIdx.x; w < total_work; w += gridDim.x, tile_par ^= 1) {
-            const Work wk = decode_work(a, w, BN);
+        long long d_tfull = 0, d_epi = 0, d_store = 0;
+        for (int64_t w = w_first; w < total_work; w += w_step, tile_par ^= 1) {
+            const Work wk = decode(w);
             const int n_chunks = (wk.num_kb + CHUNK_KB - 1) / CHUNK_KB;
 #pragma unroll
             for (int j = 0; j < HALF; ++j) acc[j] = 0.f;
+            // what the epilogue needs from global memory is requested BEFORE the accumulator drain, so its latency overlaps it
+            const int64_t row = wk.m0 + quarter * 32 + lane;
+            const int64_t col0 = wk.n0 + half * HALF;
+            const bool row_ok = row < a.M;
+            float* bs = bias_s + tile_par * BN;
+            if (a.bias != nullptr && tid < BN) bs[tid] = wk.n0 + tid < a.N ? __ldg(a.bias + wk.n0 + tid) : 0.f;
+            uint32_t mbits[HALF / 32];
+            if (MASK == 2) {
+                const uint32_t* mrow = a.mask + row * a.ldm + col0 / 32;
+#pragma unroll
+                for (int q = 0; q < HALF / 32; ++q) mbits[q] = (row_ok && col0 + 32 * q < a.N) ? __ldg(mrow + q) : 0u;
+            }
             for (int c = 0; c < n_chunks; ++c, ++gc) {
                 const uint32_t buf = gc & 1;
-                mbar_wait(tfull0 + 8 * buf, (gc >> 1) & 1);
+                mbar_wait_timed(tfull0 + 8 * buf, (gc >> 1) & 1, tid == 0 ? a.dbg : nullptr, d_tfull);
                 tc_fence_after();
 #pragma unroll
                 for (int q = 0; q < HALF / 16; ++q) {
@@ -581,50 +672,54 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(TcArgs a) {
                 __syncwarp();
                 if (lane == 0) mbar_arrive(tempty0 + 8 * buf);
             }
-            // ---- epilogue on this thread's [row, n0 + half*HALF .. +HALF); the MMA warp is already on the next tile
-            const int64_t row = wk.m0 + quarter * 32 + lane;
-            const int64_t col0 = wk.n0 + half * HALF;
-            const bool row_ok = row < a.M;
-            float* bs = bias_s + tile_par * BN;
-            if (tid < BN) bs[tid] = (a.bias != nullptr && wk.n0 + tid < a.N) ? __ldg(a.bias + wk.n0 + tid) : 0.f;
-            asm volatile("bar.sync 1, 256;" ::: "memory");
-            const float slope = a.act == 1 ? PS_LEAKY_SLOPE : 1.f;
-            float ss = 0.f;
+            // ---- epilogue on this thread's [row, n0 + half*HALF .. +HALF); the MMA warp is already on the next tile.
+            // (Measured with ps_gemm_tc_trace: the accumulate warps spent 60-85 % of the kernel here and the MMA thread
+            // 37-56 % waiting for them to free an accumulator, so this code is kept lean: nothing per element that the
+            // call does not ask for, shared-memory accesses as LDS/STS, store mode chosen once per tile.)
+            const long long d_e0 = (a.dbg && tid == 0) ? clock64() : 0;
+            if (a.bias != nullptr) {
+                asm volatile("bar.sync 1, 256;" ::: "memory");  // bs was filled before the drain
+                const float4* b4 = reinterpret_cast<const float4*>(bs + half * HALF);
 #pragma unroll
-            for (int j = 0; j < HALF; ++j) {
-                float x = acc[j] + bs[half * HALF + j];
-                x = x > 0.f ? x : x * slope;
-                acc[j] = x;
-                ss = fmaf(x, (col0 + j < a.N) ? x : 0.f, ss);
-            }
-            if (MASK) {  // compile-time: only the kernels launched with a sign mask carry this code
-                uint32_t* mrow = a.mask + row * a.ldm + col0 / 32;
-                if (MASK == 1) {  // record sign(activation): the backward applies leaky' from these bits
-#pragma unroll
-                    for (int q = 0; q < HALF / 32; ++q) {
-                        uint32_t bits = 0;
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) bits |= (acc[32 * q + j] > 0.f ? 1u : 0u) << j;
-                        if (row_ok && col0 + 32 * q < a.N) mrow[q] = bits;
-                    }
-                } else {  // act == 2: sum * leaky'(y), y > 0 recorded by the forward
-#pragma unroll
-                    for (int q = 0; q < HALF / 32; ++q) {
-                        const uint32_t bits = (row_ok && col0 + 32 * q < a.N) ? __ldg(mrow + q) : 0u;
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) acc[32 * q + j] *= ((bits >> j) & 1u) ? 1.f : PS_LEAKY_SLOPE;
-                    }
+                for (int j = 0; j < HALF / 4; ++j) {
+                    const float4 b = b4[j];
+                    acc[4 * j] += b.x; acc[4 * j + 1] += b.y; acc[4 * j + 2] += b.z; acc[4 * j + 3] += b.w;
                 }
+            }
+            if (a.act == 1) {
+#pragma unroll
+                for (int j = 0; j < HALF; ++j) acc[j] = fmaxf(acc[j], acc[j] * PS_LEAKY_SLOPE);  // leaky_relu, slope < 1
+            }
+            if (MASK == 1) {  // record sign(activation): the backward applies leaky' from these bits
+                uint32_t* mrow = a.mask + row * a.ldm + col0 / 32;
+#pragma unroll
+                for (int q = 0; q < HALF / 32; ++q) {
+                    uint32_t bits = 0;
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) bits |= (acc[32 * q + j] > 0.f ? 1u : 0u) << j;
+                    if (row_ok && col0 + 32 * q < a.N) mrow[q] = bits;
+                }
+            } else if (MASK == 2) {  // act == 2: sum * leaky'(y), y > 0 recorded by the forward (words loaded before the drain)
+#pragma unroll
+                for (int q = 0; q < HALF / 32; ++q)
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) acc[32 * q + j] *= ((mbits[q] >> j) & 1u) ? 1.f : PS_LEAKY_SLOPE;
             }
             float inv_norm = 1.f;
             if (a.l2norm) {  // the row is split over two threads (column halves): combine through shared memory
+                float ss = 0.f;
+#pragma unroll
+                for (int j = 0; j < HALF; ++j) ss = fmaf(acc[j], (col0 + j < a.N) ? acc[j] : 0.f, ss);
                 float* sb = ss_buf + tile_par * 256;
                 sb[half * 128 + quarter * 32 + lane] = ss;
                 asm volatile("bar.sync 1, 256;" ::: "memory");
                 const float nrm = sqrtf(sb[quarter * 32 + lane] + sb[128 + quarter * 32 + lane]);
                 inv_norm = 1.f / nrm;
                 if (half == 0 && row_ok && a.norm_out) a.norm_out[row] = nrm;
+#pragma unroll
+                for (int j = 0; j < HALF; ++j) acc[j] *= inv_norm;
             }
+            const long long d_e1 = (a.dbg && tid == 0) ? clock64() : 0;
             // Stores go through a per-warp shared-memory transpose, 16 columns at a time: a thread owns one output
             // row, and writing it directly would touch 32 rows x 16 B per instruction (half sectors, 32 LSU
             // wavefronts).  Staged, an instruction writes 8 rows x 64 contiguous bytes (full sectors).
@@ -632,40 +727,58 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(TcArgs a) {
                 float* wb = epi_buf + warp * (32 * kEpiStride);
                 const int rr = lane >> 2, cc = (lane & 3) * 4;
                 const int64_t row_base = wk.m0 + quarter * 32;
+                const int mode = a.accumulate ? 1 : ((MASK == 0 && a.act == 2) ? 2 : 0);  // uniform over the tile
+                float* dst0 = a.C + (row_base + rr) * a.ldc + col0 + cc;
+                const int64_t step8 = 8 * a.ldc;
+                bool ok[4];
+#pragma unroll
+                for (int p8 = 0; p8 < 4; ++p8) ok[p8] = row_base + 8 * p8 + rr < a.M;
 #pragma unroll
                 for (int blk = 0; blk < HALF / 16; ++blk) {
 #pragma unroll
                     for (int q = 0; q < 4; ++q)
                         *reinterpret_cast<float4*>(wb + lane * kEpiStride + 4 * q) =
-                            make_float4(acc[16 * blk + 4 * q] * inv_norm, acc[16 * blk + 4 * q + 1] * inv_norm,
-                                        acc[16 * blk + 4 * q + 2] * inv_norm, acc[16 * blk + 4 * q + 3] * inv_norm);
+                            make_float4(acc[16 * blk + 4 * q], acc[16 * blk + 4 * q + 1], acc[16 * blk + 4 * q + 2], acc[16 * blk + 4 * q + 3]);
                     __syncwarp();
-                    const int64_t gcol = col0 + 16 * blk + cc;
+                    const bool col_ok = col0 + 16 * blk + cc < a.N;  // N % 4 == 0: a float4 is all-or-nothing
+                    float* dst = dst0 + 16 * blk;
+                    float4 v[4];
 #pragma unroll
-                    for (int p8 = 0; p8 < 4; ++p8) {
-                        const int r = 8 * p8 + rr;
-                        const float4 v = *reinterpret_cast<const float4*>(wb + r * kEpiStride + cc);
-                        const int64_t grow = row_base + r;
-                        if (grow < a.M && gcol < a.N) {  // N % 4 == 0: a float4 is all-or-nothing
-                            float* dst = a.C + grow * a.ldc + gcol;
-                            if (a.accumulate) {
-                                atomicAdd(dst + 0, v.x); atomicAdd(dst + 1, v.y); atomicAdd(dst + 2, v.z); atomicAdd(dst + 3, v.w);
-                            } else if (MASK == 0 && a.act == 2) {  // C holds leaky_relu outputs y: C = acc * leaky'(y)
-                                const float4 y = *reinterpret_cast<const float4*>(dst);
-                                *reinterpret_cast<float4*>(dst) = make_float4(v.x * ps_leaky_grad_from_out(y.x), v.y * ps_leaky_grad_from_out(y.y),
-                                                                              v.z * ps_leaky_grad_from_out(y.z), v.w * ps_leaky_grad_from_out(y.w));
-                            } else {
-                                *reinterpret_cast<float4*>(dst) = v;
+                    for (int p8 = 0; p8 < 4; ++p8) v[p8] = *reinterpret_cast<const float4*>(wb + (8 * p8 + rr) * kEpiStride + cc);
+                    if (mode == 0) {
+#pragma unroll
+                        for (int p8 = 0; p8 < 4; ++p8)
+                            if (ok[p8] && col_ok) *reinterpret_cast<float4*>(dst + p8 * step8) = v[p8];
+                    } else if (mode == 1) {  // split-K partials
+#pragma unroll
+                        for (int p8 = 0; p8 < 4; ++p8)
+                            if (ok[p8] && col_ok) {
+                                float* d = dst + p8 * step8;
+                                atomicAdd(d + 0, v[p8].x); atomicAdd(d + 1, v[p8].y); atomicAdd(d + 2, v[p8].z); atomicAdd(d + 3, v[p8].w);
                             }
-                        }
+                    } else {  // C holds leaky_relu outputs y: C = acc * leaky'(y)
+#pragma unroll
+                        for (int p8 = 0; p8 < 4; ++p8)
+                            if (ok[p8] && col_ok) {
+                                float* d = dst + p8 * step8;
+                                const float4 y = *reinterpret_cast<const float4*>(d);
+                                *reinterpret_cast<float4*>(d) = make_float4(v[p8].x * ps_leaky_grad_from_out(y.x), v[p8].y * ps_leaky_grad_from_out(y.y),
+                                                                            v[p8].z * ps_leaky_grad_from_out(y.z), v[p8].w * ps_leaky_grad_from_out(y.w));
+                            }
                     }
                     __syncwarp();
                 }
             }
+            if (a.dbg && tid == 0) { const long long d_e2 = clock64(); d_epi += d_e2 - d_e0; d_store += d_e2 - d_e1; }
         }
+        if (a.dbg && tid == 0) { a.dbg[blockIdx.x * 8 + 5] = d_tfull; a.dbg[blockIdx.x * 8 + 6] = d_epi; a.dbg[blockIdx.x * 8 + 7] = d_store; }
         tc_fence_before();
     }
     __syncthreads();
+    if (CL > 1) {  // nobody leaves while the peer may still signal its barriers or write its stages
+        asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+        asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+    }
     if (warp == 16) { tc_fence_after(); tmem_dealloc<2 * BN>(tmem_base); }
 }
 
@@ -729,12 +842,12 @@ static int pack_scratch(cudaStream_t stream, size_t bytes, void** out) {
     return PS_OK;
 }
 
-template <bool PK, bool QK, int BN, bool BPACK, int MASK = 0>
+template <bool PK, bool QK, int BN, bool BPACK, int MASK = 0, int CL = 1>
 int launch_tc(TcArgs a, int q_kmajor, cudaStream_t stream) {
     constexpr int STAGES = BN == 256 ? 2 : 3;
     constexpr size_t smem = STAGES * (2 * BM * 128 + 2 * BN * 128) + (2 * STAGES + 4) * 8 + 16 + (2 * 2 * 128 + 2 * BN + 8 * 32 * kEpiStride) * 4 + 1024;
     static_assert(smem <= 232448, "shared memory budget");
-    auto kern = gemm_tc_kernel<PK, QK, BN, BPACK, MASK>;
+    auto kern = gemm_tc_kernel<PK, QK, BN, BPACK, MASK, CL>;
     static bool configured = false;
     static int sms = 148;
     if (!configured) {
@@ -761,6 +874,22 @@ int launch_tc(TcArgs a, int q_kmajor, cudaStream_t stream) {
     const int64_t usable = sms - g_tc_reserve > 1 ? sms - g_tc_reserve : 1;  // SMs left free for other streams
     int64_t grid64 = total < usable ? total : usable;
     if (g_tc_waves > 1 && total >= static_cast<int64_t>(sms) * 8 * g_tc_waves) grid64 = static_cast<int64_t>(sms) * g_tc_waves;
+    if (CL > 1) {  // one cluster per tile pair: an even grid, at most one CTA per SM
+        const int64_t pairs = ps_ceil_div(a.mt, CL) * a.nt;
+        int64_t clusters = usable / CL;
+        if (clusters > pairs) clusters = pairs;
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(static_cast<unsigned>(clusters * CL));
+        cfg.blockDim = dim3(kThreads);
+        cfg.dynamicSmemBytes = smem;
+        cfg.stream = stream;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr; cfg.numAttrs = 1;
+        PS_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, a));
+        return PS_OK;
+    }
     const unsigned grid = static_cast<unsigned>(grid64);
     kern<<<grid, kThreads, smem, stream>>>(a);
     PS_LAUNCH_CHECK();
@@ -771,7 +900,21 @@ int launch_tc(TcArgs a, int q_kmajor, cudaStream_t stream) {
 
 extern "C" int ps_gemm_tc_reserve_sms(int n) { const int old = g_tc_reserve; if (n >= 0 && n <= 64) g_tc_reserve = n; return old; }
 extern "C" int ps_gemm_tc_waves(int waves) { const int old = g_tc_waves; if (waves >= 1 && waves <= 64) g_tc_waves = waves; return old; }
+extern "C" int ps_gemm_tc_prefetch(int on) {
+    int old = 0;
+    if (cudaMemcpyFromSymbol(&old, g_tc_prefetch, sizeof(int)) != cudaSuccess) return PS_ERR_CUDA;
+    const int v = on != 0;
+    if (cudaMemcpyToSymbol(g_tc_prefetch, &v, sizeof(int)) != cudaSuccess) return PS_ERR_CUDA;
+    return old;
+}
+static unsigned long long* g_tc_dbg = nullptr;
+// development: buf = device array of 8 counters per CTA (148 x 8), filled by the next tensor-core GEMM launches:
+// [0] MMA thread total cycles, [1] its wait for operands (full), [2] its wait for a free TMEM buffer, [3] weight-stream wait
+// for a free stage, [4] producer wait for a free stage, [5] accumulate-warp wait for a finished chunk, [6] epilogue cycles
+extern "C" int ps_gemm_tc_trace(unsigned long long* buf) { g_tc_dbg = buf; return PS_OK; }
 static bool g_tc_pack = true;
+static bool g_tc_cluster = true;
+extern "C" int ps_gemm_tc_cluster(int on) { const int old = g_tc_cluster; if (on == 0 || on == 1) g_tc_cluster = on != 0; return old; }
 extern "C" int ps_gemm_tc_pack(int on) { const int old = g_tc_pack; if (on == 0 || on == 1) g_tc_pack = on != 0; return old; }
 
 // Returns PS_ERR_UNSUPPORTED (without setting an error) when the shape is outside what this
@@ -801,7 +944,7 @@ int ps_gemm_tc_launch(const float* P, int64_t ldp, int p_kmajor, const int32_t* 
     if (!accumulate && K > 4 * kMaxChainK) return PS_ERR_UNSUPPORTED;
     if (accumulate && ps_ceil_div(K, splits < 1 ? 1 : splits) > kMaxChainK) splits = static_cast<int>(ps_ceil_div(K, kMaxChainK));
     const int BN = (N > 128) ? 256 : 128;
-    TcArgs a{P, ldp, p_rows, Q, ldq, q_rows, C, ldc, M, N, K, bias, norm_out, act, l2norm, accumulate, 0, 0, 0, 0, nullptr, mask, ldm, p_colsum};
+    TcArgs a{P, ldp, p_rows, Q, ldq, q_rows, C, ldc, M, N, K, bias, norm_out, act, l2norm, accumulate, 0, 0, 0, 0, nullptr, mask, ldm, g_tc_dbg, p_colsum};
     const int64_t num_kb = ps_ceil_div(K, BK);
     if (splits < 1) splits = 1;
     a.kb_per_split = static_cast<int>(ps_ceil_div(num_kb, splits));
@@ -810,14 +953,21 @@ int ps_gemm_tc_launch(const float* P, int64_t ldp, int p_kmajor, const int32_t* 
     a.nt = ps_ceil_div(N, BN);
     // weight operand (no gather, no split-K) against a tall K-major activation: pre-packed hi/lo images + bulk copies
     const bool packable = p_kmajor && q_rows == nullptr && !accumulate && a.zs == 1;
+    // tile PAIRS (2-CTA clusters sharing the weight stream by multicast) once there are enough tiles to fill the SMs with pairs
+    const bool pairs = g_tc_cluster && a.mt * a.nt >= 2 * 148;
     if (mask != nullptr) {  // the sign-mask epilogue lives in the packed-weight kernels only
         if (!packable) return PS_ERR_UNSUPPORTED;
-        if (act == 1)
+        if (act == 1) {
+            if (pairs) return BN == 256 ? launch_tc<true, true, 256, true, 1, 2>(a, q_kmajor, stream) : launch_tc<true, true, 128, true, 1, 2>(a, q_kmajor, stream);
             return BN == 256 ? launch_tc<true, true, 256, true, 1>(a, q_kmajor, stream) : launch_tc<true, true, 128, true, 1>(a, q_kmajor, stream);
+        }
+        if (pairs) return BN == 256 ? launch_tc<true, true, 256, true, 2, 2>(a, q_kmajor, stream) : launch_tc<true, true, 128, true, 2, 2>(a, q_kmajor, stream);
         return BN == 256 ? launch_tc<true, true, 256, true, 2>(a, q_kmajor, stream) : launch_tc<true, true, 128, true, 2>(a, q_kmajor, stream);
     }
-    if (g_tc_pack && packable && M >= 1024)
+    if (g_tc_pack && packable && M >= 1024) {
+        if (pairs) return BN == 256 ? launch_tc<true, true, 256, true, 0, 2>(a, q_kmajor, stream) : launch_tc<true, true, 128, true, 0, 2>(a, q_kmajor, stream);
         return BN == 256 ? launch_tc<true, true, 256, true>(a, q_kmajor, stream) : launch_tc<true, true, 128, true>(a, q_kmajor, stream);
+    }
 #define PS_TC_CASE(pk, qk)                                                         \
     if (static_cast<bool>(p_kmajor) == pk && static_cast<bool>(q_kmajor) == qk)     \
         return BN == 256 ? launch_tc<pk, qk, 256, false>(a, q_kmajor, stream) : launch_tc<pk, qk, 128, false>(a, q_kmajor, stream);

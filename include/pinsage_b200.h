@@ -113,6 +113,17 @@ int ps_gemm_tc_waves(int waves);
 /* Tuning knob: the persistent tensor-core GEMMs leave n SMs free (default 0) so that kernels of other streams (the
  * batch preparation of the next training step) never wait for a GEMM to retire.  Returns the previous value. */
 int ps_gemm_tc_reserve_sms(int n);
+/* 1 (default) = the tensor-core producers prefetch their next operand rows into L2 (a tile / 6 k-blocks ahead), 0 = off
+ * (A/B measurements).  Returns the previous setting. */
+int ps_gemm_tc_prefetch(int on);
+/* 1 (default) = tall packed-weight GEMMs run as 2-CTA clusters on tile pairs that share the weight stream by TMA
+ * multicast, 0 = one CTA per tile (A/B measurements).  Returns the previous setting. */
+int ps_gemm_tc_cluster(int on);
+/* Development: device array of 8 uint64 counters per CTA that the following tensor-core GEMM launches fill with the
+ * cycles their warp roles spent waiting (NULL = off): [0] MMA-issue total, [1] its wait for operands, [2] its wait for a
+ * free accumulator, [3] weight-stream wait for a free stage, [4] producer wait for a free stage, [5] accumulate-warp
+ * wait for a finished chunk, [6] epilogue. */
+int ps_gemm_tc_trace(unsigned long long* buf);
 
 /* ---- K4+K6: neighbour gather + importance-weighted mean fused with the concat
  *      (pinsage_model.py:195-197,202,208):

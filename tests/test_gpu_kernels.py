@@ -402,3 +402,38 @@ def test_flat_adam_equals_torch_adam():
     for pa, pb in zip(a.parameters(), b.parameters()):
         assert rel(pb, pa) < 1e-6
     assert oa.param_groups[0]["lr"] == ob.param_groups[0]["lr"]
+
+
+@pytest.mark.parametrize("M,N,K", [(40_001 // 4 * 4, 512, 256), (38_000, 128, 768), (37_900, 512, 128), (75_000, 256, 64)])
+def test_gemm_tile_pairs_with_multicast_weights(nat, M, N, K):
+    """Tall packed-weight GEMMs run as 2-CTA clusters on tile PAIRS that share the weight stream by TMA multicast
+    (odd tile counts leave a phantom second tile): forward with row gather + bias + leaky + sign mask, the act=2 backward
+    with that mask, the l2norm epilogue -- against fp64 products, and bit-equal to the one-CTA-per-tile kernel."""
+    torch.manual_seed(M + N)
+    table = torch.randn(M + 5000, K, device="cuda")
+    rows = torch.randint(0, M + 5000, (M,), device="cuda", dtype=torch.int32)
+    W = torch.randn(N, K, device="cuda") * 0.1; b = torch.randn(N, device="cuda")
+    outs = {}
+    for cl in (1, 0):
+        old = nat.lib().ps_gemm_tc_cluster(cl)
+        y = torch.empty(M, N, device="cuda"); mask = torch.zeros(M, N // 32, dtype=torch.int32, device="cuda")
+        nat.gemm(table, W, y, M, N, K, p_rows=rows, bias=b, act=1, mask=mask)
+        S = torch.randn(M, 64, device="cuda", generator=torch.Generator(device="cuda").manual_seed(1)); V = torch.randn(64, N, device="cuda", generator=torch.Generator(device="cuda").manual_seed(2))
+        d = torch.full((M, N), float("nan"), device="cuda")
+        nat.gemm(S, V, d, M, N, 64, q_kmajor=False, act=2, mask=mask)
+        out = None
+        if N <= 256:
+            out = torch.empty(M, N, device="cuda"); norm = torch.empty(M, device="cuda")
+            nat.gemm(table, W, out, M, N, K, p_rows=rows, bias=b, act=1, l2norm=True, norm_out=norm)
+        outs[cl] = (y, mask, d, out)
+        nat.lib().ps_gemm_tc_cluster(old)
+    y, mask, d, out = outs[1]
+    want = leaky(table[rows.long()].double() @ W.double().t() + b.double())
+    assert rel(y, want) < 1e-5
+    bits = ((mask.view(M, N // 32, 1) >> torch.arange(32, device="cuda", dtype=torch.int32)) & 1).reshape(M, N).bool()
+    assert torch.equal(bits, y > 0)
+    assert rel(d, (S.double() @ V.double()) * torch.where(y > 0, 1.0, 0.01).double()) < 1e-5
+    if out is not None:
+        assert rel(out, want / want.norm(dim=1, keepdim=True)) < 1e-5
+    for a_, b_ in zip(outs[1], outs[0]):
+        assert (a_ is None and b_ is None) or torch.equal(a_, b_)   # same arithmetic per output element

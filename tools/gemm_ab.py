@@ -1,0 +1,42 @@
+"""Development aid (GPU): the three big GEMM shapes of a cfg3 step timed alone with the L2 prefetch off / on."""
+import os, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "gcn-song-embeddings_b200"))
+import torch, ps_native as nat
+torch.manual_seed(0)
+N, nz, din, dh, do = 1_000_000, 656_000, 256, 512, 128
+feats = torch.randn(N, din, device="cuda")
+zrows = torch.sort(torch.randperm(N, device="cuda")[:nz]).values.to(torch.int32)
+Qw = torch.randn(dh, din, device="cuda") * 0.05; Qb = torch.randn(dh, device="cuda")
+Ww = torch.randn(do, din + dh, device="cuda") * 0.05
+z = torch.empty(nz, dh, device="cuda"); mask = torch.empty(nz, dh // 32, dtype=torch.int32, device="cuda")
+s_buf = torch.randn(nz, do, device="cuda")
+gQ = torch.zeros(dh, din, device="cuda"); gb = torch.zeros(dh, device="cuda")
+flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+
+def timed(fn, reps=5):
+    ts = []
+    for _ in range(reps + 2):
+        flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); fn(); e1.record(); torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1))
+    return sorted(ts[2:])[len(ts[2:]) // 2]
+
+calls = {
+    "q_fwd_l0   [656k x 512 x 256] gather+mask": lambda: nat.gemm(feats, Qw, z, nz, dh, din, p_rows=zrows, bias=Qb, act=1, mask=mask),
+    "agg_dgrad  [656k x 512 x 128] act2 mask  ": lambda: nat.gemm(s_buf, Ww[:, din:], z, nz, dh, do, q_kmajor=False, act=2, mask=mask),
+    "q_wgrad_l0 [512 x 256 x 656k] gather     ": lambda: nat.gemm_wgrad(z, feats, gQ, dh, din, nz, x_rows=zrows, splits=74, bias_grad=gb),
+}
+import sys
+dbg = torch.zeros(148 * 8, dtype=torch.int64, device="cuda")
+for cl in (1,):
+    nat.lib().ps_gemm_tc_cluster(cl)
+    print("cluster", cl, {k: round(timed(f), 4) for k, f in calls.items()})
+    for k, f in calls.items():
+        if "wgrad" in k:
+            continue
+        dbg.zero_(); nat.lib().ps_gemm_tc_trace(dbg.data_ptr()); f(); torch.cuda.synchronize(); nat.lib().ps_gemm_tc_trace(None)
+        d = dbg.view(148, 8).double().mean(0).tolist()
+        print("   ", k, "MMA-thread total %.0f kcyc | waits: operands %.0f%%, free TMEM %.0f%% | B-stream wait-empty %.0f%% | producer wait-empty %.0f%% | acc-warp wait-tfull %.0f%%, epilogue %.0f%% (of which the staged stores %.0f%%)"
+              % (d[0] / 1e3, 100 * d[1] / d[0], 100 * d[2] / d[0], 100 * d[3] / d[0], 100 * d[4] / d[0], 100 * d[5] / d[0], 100 * d[6] / d[0], 100 * d[7] / d[0]))
