@@ -32,10 +32,18 @@ class PSGraph:
     @classmethod
     def from_edges(cls, src, dst, n_tracks, n_cols, **kw):
         """Directed edge list (both directions listed, as in graph.json) -> CSR.  Edges of a
-        source keep their listed order (stable sort), matching DGL's insertion order."""
+        source keep their listed order (stable sort), matching DGL's insertion order.
+        With a CUDA device the CSR is built in HBM by ps_csr_build (csrc/ingest.cu: one stable radix sort by
+        source + row offsets) and the handle adopts those tensors; host-only tooling (the CPU tests, dataset
+        inspection on a machine without a GPU) gets the same arrays from a numpy stable argsort."""
+        n = n_tracks + n_cols
+        if torch.cuda.is_available():
+            indptr, indices = ps_native.csr_build(torch.as_tensor(src), torch.as_tensor(dst), n)
+            g = cls(indptr.cpu(), indices.cpu(), n_tracks, n_cols, **kw)
+            g._dev_csr = (indptr, indices)  # device() adopts them instead of uploading again
+            return g
         src = np.asarray(src, dtype=np.int64)
         dst = np.asarray(dst, dtype=np.int64)
-        n = n_tracks + n_cols
         if src.size and (src.min() < 0 or src.max() >= n or dst.min() < 0 or dst.max() >= n):
             raise IndexError("edge endpoint out of range")
         order = np.argsort(src, kind="stable")
@@ -83,7 +91,9 @@ class PSGraph:
     def device(self) -> "ps_native.GraphHandle":
         """Upload once; ps_graph_create validates that every node has a successor."""
         if self._handle is None:
-            self._handle = ps_native.GraphHandle(self.indptr, self.indices, self.n_tracks, self.n_cols)
+            indptr, indices = getattr(self, "_dev_csr", None) or (self.indptr, self.indices)
+            self._handle = ps_native.GraphHandle(indptr, indices, self.n_tracks, self.n_cols)
+            self._dev_csr = None
         return self._handle
 
 

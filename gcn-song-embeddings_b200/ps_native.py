@@ -118,6 +118,8 @@ _SIGNATURES.update({
     "ps_train_step": ([ctypes.POINTER(StepArgsC), c_void_p], c_int),
     "ps_profile_enable": ([c_int], c_int),
     "ps_profile_dump": ([c_char_p, c_int64], c_int64),
+    "ps_csr_build": ([c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_void_p], c_int),
+    "ps_standardize": ([c_void_p, c_int64, c_int64, c_int, c_double, c_void_p, c_void_p, c_void_p], c_int),
 })
 
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)
@@ -532,6 +534,34 @@ def topk_rows(x, k):
     idx = torch.empty((n, k), dtype=torch.int64, device="cuda")
     check(lib().ps_topk_rows(_p(x, torch.float32), _ld(x), int(n), int(m), int(k), _p(val), _p(idx), _stream()))
     return val, idx
+
+
+def csr_build(src, dst, n_nodes):
+    """ps_csr_build: (indptr int64 [n_nodes + 1], indices int32 [E]) on the device from a directed edge list; edges of a
+    source keep their listed order.  Raises IndexError on endpoints outside [0, n_nodes)."""
+    _ensure_device()
+    src = torch.as_tensor(src).to("cuda", torch.int64).contiguous()
+    dst = torch.as_tensor(dst).to("cuda", torch.int64).contiguous()
+    if src.shape != dst.shape or src.dim() != 1:
+        raise ValueError("src / dst must be 1-D and of equal length")
+    indptr = torch.empty(int(n_nodes) + 1, dtype=torch.int64, device="cuda")
+    indices = torch.empty(src.numel(), dtype=torch.int32, device="cuda")
+    rc = lib().ps_csr_build(_p(src), _p(dst), int(src.numel()), int(n_nodes), _p(indptr), _p(indices), _stream())
+    if rc == PS_ERR_RANGE:
+        raise IndexError("edge endpoint out of range")
+    check(rc)
+    return indptr, indices
+
+
+def standardize_(x, eps=1e-12):
+    """ps_standardize in place on a float32 [n, d] device tensor; returns (mean [d], std + eps [d])."""
+    _ensure_device()
+    if x.dim() != 2:
+        raise ValueError("expected a [n, d] matrix")
+    mean = torch.empty(x.shape[1], dtype=torch.float32, device="cuda")
+    std = torch.empty(x.shape[1], dtype=torch.float32, device="cuda")
+    check(lib().ps_standardize(_p(x, torch.float32), _ld(x), int(x.shape[0]), int(x.shape[1]), float(eps), _p(mean), _p(std), _stream()))
+    return mean, std
 
 
 def train_diagnostics(feats, batch, emb, triples, feat_margin, out2):

@@ -21,73 +21,83 @@ from os import path
 import numpy as np
 import torch
 
+import ps_native
 from ps_graph import PSGraph
 
 
+def standardize_features(features):
+    """(x - mean) / (std_unbiased + 1e-12) per column (spotify_graph.py:77-79).  With a CUDA device the statistics
+    and the division run in HBM (ps_standardize, csrc/ingest.cu: fp64 column sums, two passes) and the standardised
+    table comes back in the caller's placement (the trainer uploads it once anyway); without one, the same
+    formula in framework ops (host-only tooling and the CPU tests)."""
+    if torch.cuda.is_available() and features.dim() == 2 and features.shape[0] > 1:
+        x = features.to("cuda", torch.float32, copy=True).contiguous()
+        ps_native.standardize_(x, 1e-12)
+        return x if features.is_cuda else x.cpu()
+    mean = features.mean(dim=0)
+    std = features.std(dim=0, unbiased=True) + 1e-12
+    return (features - mean) / std
+
+
+def _read_json(file_path):
+    with open(file_path, "r", encoding="utf-8") as f:
+        return json.load(f)
+
+
 class SpotifyGraph():
+    """Reads a dataset directory written by the reference's crawler; attribute names are the reference's
+    (eval.py / dashboard.py read `tracks`, `collections`, `graph`, `base_dir`, `nbhds_path`, `features`, ...)."""
 
     def __init__(self, dir, features_dir):
         self.base_dir = dir
-        self.nbhds_path = os.path.join(self.base_dir, "neighborhoods.pt")
-        self.tracks_pth = path.join(dir, "tracks.json")
-        self.col_pth = path.join(dir, "collections.json")
-        self.graph_pth = path.join(dir, "graph.json")
-        self.img_dir = path.join(dir, "images")
-        self.clip_dir = path.join(dir, "clips")
+        join = lambda name: path.join(dir, name)
+        self.nbhds_path = join("neighborhoods.pt")
+        self.tracks_pth, self.col_pth, self.graph_pth = join("tracks.json"), join("collections.json"), join("graph.json")
+        self.img_dir, self.clip_dir = join("images"), join("clips")
         print("Loading graph...")
-        with open(self.tracks_pth, "r", encoding="utf-8") as f:
-            self.tracks = json.load(f)
-        with open(self.col_pth, "r", encoding="utf-8") as f:
-            self.collections = json.load(f)
-        with open(self.graph_pth, "r", encoding="utf-8") as f:
-            self.graph = json.load(f)
+        self.tracks = _read_json(self.tracks_pth)
+        self.collections = _read_json(self.col_pth)
+        self.graph = _read_json(self.graph_pth)
         self.ft_dir = features_dir if features_dir is not None and os.path.isdir(features_dir) else None
         self.features_dict = {}
+        self._node_index = None
+
+    def _index(self):
+        """id -> node number: position in list(tracks) + list(collections) (spotify_graph.py:43-46,58)."""
+        if self._node_index is None:
+            self._node_index = {nid: i for i, nid in enumerate(list(self.tracks) + list(self.collections))}
+        return self._node_index
 
     def to_dgl_graph(self):
-        """(g, track_ids, col_ids, features): nodes are numbered by position in
-        list(tracks) + list(collections); edges as listed; features standardised per column
-        with the unbiased std + 1e-12 (spotify_graph.py:41-85)."""
-        track_ids = list(self.tracks)
-        col_ids = list(self.collections)
-        index_map = {nid: i for i, nid in enumerate(track_ids + col_ids)}
-        edges = self.graph["edges"]
-        src = np.fromiter((index_map[e["from"]] for e in edges), dtype=np.int64, count=len(edges))
-        dst = np.fromiter((index_map[e["to"]] for e in edges), dtype=np.int64, count=len(edges))
-        g = PSGraph.from_edges(src, dst, len(track_ids), len(col_ids), nbhds_path=self.nbhds_path, base_dir=self.base_dir)
+        """(g, track_ids, col_ids, features): edges as listed (CSR built on the device, ps_csr_build); features
+        standardised per column with the unbiased std + 1e-12 (ps_standardize) (spotify_graph.py:41-85)."""
+        track_ids, col_ids = list(self.tracks), list(self.collections)
+        index, edges = self._index(), self.graph["edges"]
+        ends = np.fromiter((index[e[k]] for e in edges for k in ("from", "to")), dtype=np.int64, count=2 * len(edges)).reshape(-1, 2)
+        g = PSGraph.from_edges(ends[:, 0], ends[:, 1], len(track_ids), len(col_ids), nbhds_path=self.nbhds_path, base_dir=self.base_dir)
+        features = None
         if self.ft_dir:
-            features = torch.stack([torch.load(os.path.join(self.ft_dir, t + ".pt")) for t in track_ids], dim=0)
-            mean = features.mean(dim=0)
-            std = features.std(dim=0, unbiased=True) + 1e-12
-            features = (features - mean) / std
-        else:
-            features = None
+            features = standardize_features(torch.stack([torch.load(path.join(self.ft_dir, t + ".pt")) for t in track_ids], dim=0))
         self.g, self.track_ids, self.col_ids, self.features = g, track_ids, col_ids, features
         return g, track_ids, col_ids, features
 
     def load_positives(self, pos_pth):
-        """int64 [P, 2] index pairs (spotify_graph.py:88-100)."""
-        with open(pos_pth, "r", encoding="utf-8") as f:
-            positives = json.load(f)
-        index_map = {nid: i for i, nid in enumerate(list(self.tracks))}
-        a = torch.tensor([index_map[pair["a"]] for pair in positives], dtype=torch.int64)
-        b = torch.tensor([index_map[pair["b"]] for pair in positives], dtype=torch.int64)
-        pos = torch.stack((a, b), dim=1)
-        self.positives = pos
-        return pos
+        """int64 [P, 2] node-number pairs of the {"a": id, "b": id} records (spotify_graph.py:88-100)."""
+        pairs, index = _read_json(pos_pth), self._index()  # tracks come first, so node number == track number
+        flat = np.fromiter((index[p[k]] for p in pairs for k in ("a", "b")), dtype=np.int64, count=2 * len(pairs))
+        self.positives = torch.from_numpy(flat.reshape(-1, 2).copy())
+        return self.positives
 
     def load_positives_split(self, pos_pth, split=0.7, shuffle=True, random_seed=42):
-        """(train, test): RandomState(random_seed).permutation, first `split` fraction trains
+        """(train, test): rows permuted by RandomState(random_seed), the first `split` fraction trains
         (spotify_graph.py:102-110)."""
         pos = self.load_positives(pos_pth)
-        n = pos.shape[0]
         if shuffle:
-            index = np.random.RandomState(random_seed).permutation(n)
-            pos = pos[index, :]
-        cut_point = int(split * n)
-        return pos[:cut_point, :], pos[cut_point:, :]
+            pos = pos[torch.from_numpy(np.random.RandomState(random_seed).permutation(pos.shape[0]))]
+        cut = int(split * pos.shape[0])
+        return pos[:cut], pos[cut:]
 
     def song_info(self, index_id):
-        track_ids = list(self.tracks)
-        t = self.tracks[track_ids[index_id]]
-        return f"{t.get('name', track_ids[index_id])} - {t.get('artist', '')}"
+        tid = list(self.tracks)[index_id]
+        t = self.tracks[tid]
+        return f"{t.get('name', tid)} - {t.get('artist', '')}"

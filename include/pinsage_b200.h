@@ -310,6 +310,20 @@ int ps_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg
                  float lr, float beta1, float beta2, float eps, int64_t step, float grad_scale,
                  ps_stream_t stream);
 
+/* ---- ingest: the device side of SpotifyGraph.to_dgl_graph (spotify_graph.py:41-85).
+ *      ps_csr_build: directed edge list as listed in graph.json (both directions present, duplicates kept,
+ *      spotify_graph.py:48-63) -> CSR over n_nodes rows: indptr int64 [n_nodes + 1], indices int32 [n_edges].
+ *      One stable radix sort by source keeps the listed order inside a row (DGL's successor order).  Endpoints
+ *      outside [0, n_nodes) -> PS_ERR_RANGE (the reference's index_map raises KeyError on unknown ids).
+ *      Synchronises `stream`; temporaries come from the stream-ordered allocator (ingest runs once).
+ *      ps_standardize: x[:, j] = (x[:, j] - mean_j) / (std_j + eps) in place, std unbiased (N - 1)
+ *      (spotify_graph.py:77-79; eps = 1e-12 there); column statistics accumulated in fp64;
+ *      mean_out / std_out (float32 [d], may be NULL) receive mean_j and std_j + eps. ---- */
+int ps_csr_build(const int64_t* src, const int64_t* dst, int64_t n_edges, int64_t n_nodes,
+                 int64_t* indptr, int32_t* indices, ps_stream_t stream);
+int ps_standardize(float* x, int64_t ld, int64_t n, int d, double eps, float* mean_out, float* std_out,
+                   ps_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif
