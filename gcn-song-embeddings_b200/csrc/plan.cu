@@ -245,11 +245,23 @@ extern "C" int ps_plan_transpose(const int32_t* nbz, int64_t n_pairs, int64_t nz
 // Sizes are only known on the device, so the call synchronises `stream` L+1 times (one 4-byte read each) and lays the
 // outputs out back to back in the caller's arena; `out` receives sizes and byte offsets.  Returns PS_ERR_NOSPACE (with
 // out->bytes_needed = a size that is certainly enough for the part reached) when the arena is too small: grow and retry.
-extern "C" int ps_prepare_plan(const int64_t* batch, int64_t B, const int32_t* tab_nodes, const float* tab_w, int64_t n_ids, int Tp,
-                               int T, int n_layers, int need_backward, void* arena_, int64_t arena_bytes, ps_plan_desc* out,
-                               ps_stream_t stream_) {
+namespace {
+// where a layer's neighbourhoods come from: the precomputed table (reference default) or the walker run on the
+// layer's targets (online sampling, pinsage_model.py:142-154)
+struct NeighbourSource {
+    const int32_t* tab_nodes; const float* tab_w; int Tp;         // table
+    const ps_graph_t* graph; int n_hops; double alpha; uint64_t seed;  // walker (graph != nullptr)
+};
+}  // namespace
+
+static int prepare_plan_impl(const int64_t* batch, int64_t B, const NeighbourSource& nsrc, int64_t n_ids,
+                             int T, int n_layers, int need_backward, void* arena_, int64_t arena_bytes, ps_plan_desc* out,
+                             ps_stream_t stream_) {
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-    PS_REQUIRE(batch && tab_nodes && tab_w && arena_ && out, "null pointer");
+    const int32_t* tab_nodes = nsrc.tab_nodes;
+    const float* tab_w = nsrc.tab_w;
+    const int Tp = nsrc.graph != nullptr ? T : nsrc.Tp;
+    PS_REQUIRE(batch && (nsrc.graph != nullptr || (tab_nodes && tab_w)) && arena_ && out, "null pointer");
     PS_REQUIRE(B > 0 && T > 0 && T <= Tp && n_layers >= 1 && n_layers <= PS_MAX_LAYERS, "bad shape (T must not exceed the table width)");
     PS_REQUIRE(n_ids > 0 && n_ids < (1ll << 31), "bad id space");
     memset(out, 0, sizeof(*out));
@@ -316,8 +328,13 @@ extern "C" int ps_prepare_plan(const int64_t* batch, int64_t B, const int32_t* t
         const int64_t save = ar.off;
         ok = ar.take<int32_t>(n_nb, &nb, &off_nb_tmp);
         if (!ok) PS_NOSPACE(n_nb * 12);
-        lookup_kernel<<<blocks_for(n_nb), 256, 0, stream>>>(cur, n, tab_nodes, tab_w, Tp, T, nb, w);
-        PS_LAUNCH_CHECK();
+        if (nsrc.graph != nullptr) {  // fresh neighbourhoods of this layer's targets: top-T visit counts of n_hops walk steps each
+            rc = ps_walk_topt(nsrc.graph, cur, n, nsrc.n_hops, nsrc.alpha, 0, T, nsrc.seed, nullptr, nullptr, nb, w, nullptr, stream_);
+            if (rc != PS_OK) return rc;
+        } else {
+            lookup_kernel<<<blocks_for(n_nb), 256, 0, stream>>>(cur, n, tab_nodes, tab_w, Tp, T, nb, w);
+            PS_LAUNCH_CHECK();
+        }
         PS_CUDA_CHECK(cudaMemsetAsync(flag, 0, static_cast<size_t>(n_ids + 1) * sizeof(int32_t), stream));
         mark_kernel<<<blocks_for(n_nb), 256, 0, stream>>>(nb, n_nb, cur, n, with_self ? 1 : 0, n_ids, flag);
         PS_LAUNCH_CHECK();
@@ -362,4 +379,20 @@ extern "C" int ps_prepare_plan(const int64_t* batch, int64_t B, const int32_t* t
     out->bytes_used = ar.off;
     out->bytes_needed = ar.off;
     return PS_OK;
+}
+
+extern "C" int ps_prepare_plan(const int64_t* batch, int64_t B, const int32_t* tab_nodes, const float* tab_w, int64_t n_ids, int Tp,
+                               int T, int n_layers, int need_backward, void* arena_, int64_t arena_bytes, ps_plan_desc* out,
+                               ps_stream_t stream_) {
+    PS_REQUIRE(tab_nodes && tab_w, "null pointer");
+    const NeighbourSource nsrc{tab_nodes, tab_w, Tp, nullptr, 0, 0.0, 0ull};
+    return prepare_plan_impl(batch, B, nsrc, n_ids, T, n_layers, need_backward, arena_, arena_bytes, out, stream_);
+}
+
+extern "C" int ps_prepare_plan_online(const int64_t* batch, int64_t B, const ps_graph_t* graph, int64_t n_items, int n_hops,
+                                      double alpha, uint64_t seed, int T, int n_layers, int need_backward, void* arena_,
+                                      int64_t arena_bytes, ps_plan_desc* out, ps_stream_t stream_) {
+    PS_REQUIRE(graph != nullptr, "null pointer");
+    const NeighbourSource nsrc{nullptr, nullptr, 0, graph, n_hops, alpha, seed};
+    return prepare_plan_impl(batch, B, nsrc, n_items, T, n_layers, need_backward, arena_, arena_bytes, out, stream_);
 }

@@ -169,7 +169,13 @@ def prepare_native(batch: torch.Tensor, n_layers: int, T: int, table: NeighborTa
     (ps_prepare_plan, csrc/plan.cu): what torch.unique + build_plan + count_triples compose from ~25 calls."""
     if T > table.Tp:
         raise ValueError(f"T={T} exceeds the precomputed neighbourhood width {table.Tp}")
-    arena, base, d = nat.prepare_plan(batch, table.nodes, table.w, T, n_layers, need_backward)
+    if isinstance(table, OnlineNeighbors):  # the walker runs on every layer's targets inside the same host call
+        table.new_plan()
+        with nat._Timed("prepare_plan_online"):
+            arena, base, d = nat.prepare_plan(batch, None, None, T, n_layers, need_backward,
+                                              online=(table.graph, table.n, table.n_hops, table.alpha, table._seed))
+    else:
+        arena, base, d = nat.prepare_plan(batch, table.nodes, table.w, T, n_layers, need_backward)
     B = batch.shape[0]
 
     def view(off, count, dtype, shape=None):
@@ -444,10 +450,11 @@ class Engine:
             if timing is not None:
                 side.synchronize(); t1 = time.perf_counter(); timing["sample"] += t1 - t0
             table = NeighborTable.of(m.nbhds)
-            if isinstance(table, NeighborTable) and table.nodes.is_cuda and os.environ.get("PS_PY_PREPARE") != "1":
+            native_ok = isinstance(table, OnlineNeighbors) or (isinstance(table, NeighborTable) and table.nodes.is_cuda)
+            if native_ok and os.environ.get("PS_PY_PREPARE") != "1":
                 plan, triples, counts = prepare_native(batch.contiguous(), m.n_layers, m.T, table)  # one host call
                 t2 = t1 if timing is not None else 0.0
-            else:  # online neighbourhoods (the walker runs per layer), or PS_PY_PREPARE=1: composed from Python
+            else:  # PS_PY_PREPARE=1 (or a host-resident table): composed from Python
                 top, inv = torch.unique(batch.reshape(-1), return_inverse=True)
                 if timing is not None:
                     t2 = time.perf_counter(); timing["unique"] += t2 - t1

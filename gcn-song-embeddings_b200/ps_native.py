@@ -114,6 +114,8 @@ class PlanDescC(ctypes.Structure):
 _SIGNATURES.update({
     "ps_prepare_plan": ([c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_int, c_int, c_int, c_int, c_void_p, c_int64,
                          ctypes.POINTER(PlanDescC), c_void_p], c_int),
+    "ps_prepare_plan_online": ([c_void_p, c_int64, c_void_p, c_int64, c_int, c_double, c_uint64, c_int, c_int, c_int, c_void_p, c_int64,
+                                ctypes.POINTER(PlanDescC), c_void_p], c_int),
     "ps_train_step_workspace": ([ctypes.POINTER(StepArgsC)], c_int64),
     "ps_train_step": ([ctypes.POINTER(StepArgsC), c_void_p], c_int),
     "ps_profile_enable": ([c_int], c_int),
@@ -224,13 +226,14 @@ PS_ERR_NOSPACE, PS_ERR_RANGE = -5, -6
 _arena_hint = {}  # (B, T, n_layers, n_ids) -> bytes that were enough last time
 
 
-def prepare_plan(batch, table_nodes, table_w, T, n_layers, need_backward=True):
+def prepare_plan(batch, table_nodes, table_w, T, n_layers, need_backward=True, online=None):
     """ps_prepare_plan on the current stream: (arena uint8 tensor, PlanDescC).  The arena is sized from the previous call
-    with the same shape and grown on demand (the sizes of the frontiers are only known on the device)."""
+    with the same shape and grown on demand (the sizes of the frontiers are only known on the device).
+    online = (GraphHandle, n_items, n_hops, alpha, seed): ps_prepare_plan_online, the walker instead of the table."""
     global launch_count
     _ensure_device()
     B = batch.shape[0]
-    n_ids, Tp = table_nodes.shape
+    n_ids = int(online[1]) if online is not None else table_nodes.shape[0]
     key = (B, T, n_layers, n_ids)
     size = _arena_hint.get(key, max(1 << 20, 64 * 3 * B * (T + 1) * T))
     desc = PlanDescC()
@@ -239,9 +242,15 @@ def prepare_plan(batch, table_nodes, table_w, T, n_layers, need_backward=True):
         arena = torch.empty(size + 256, dtype=torch.uint8, device="cuda")
         base = (arena.data_ptr() + 255) & ~255
         launch_count += 6 + 14 * n_layers
-        rc = lib().ps_prepare_plan(_p(batch, torch.int64), B, _p(table_nodes, torch.int32), _p(table_w, torch.float32), n_ids, Tp,
-                                   int(T), int(n_layers), int(need_backward), c_void_p(base), size, ctypes.byref(desc),
-                                   c_void_p(torch.cuda.current_stream().cuda_stream))
+        stream = c_void_p(torch.cuda.current_stream().cuda_stream)
+        if online is not None:
+            graph, _, n_hops, alpha, seed = online
+            rc = lib().ps_prepare_plan_online(_p(batch, torch.int64), B, graph._h, n_ids, int(n_hops), float(alpha), int(seed),
+                                              int(T), int(n_layers), int(need_backward), c_void_p(base), size, ctypes.byref(desc), stream)
+        else:
+            rc = lib().ps_prepare_plan(_p(batch, torch.int64), B, _p(table_nodes, torch.int32), _p(table_w, torch.float32), n_ids,
+                                       table_nodes.shape[1], int(T), int(n_layers), int(need_backward), c_void_p(base), size,
+                                       ctypes.byref(desc), stream)
         if rc == PS_ERR_NOSPACE:
             size = max(int(desc.bytes_needed), 2 * size)
             continue

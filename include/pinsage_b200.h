@@ -302,6 +302,13 @@ typedef struct ps_plan_desc {
 } ps_plan_desc;
 int ps_prepare_plan(const int64_t* batch, int64_t B, const int32_t* table_nodes, const float* table_w, int64_t n_ids, int Tp,
                     int T, int n_layers, int need_backward, void* arena, int64_t arena_bytes, ps_plan_desc* out, ps_stream_t stream);
+/* The same preparation with ONLINE neighbourhoods (relevant_nodes_per_layer, pinsage_model.py:142-154): instead of a
+ * table lookup, ps_walk_topt runs on every layer's targets (n_hops steps each, restart probability alpha, Philox key
+ * `seed`; a node that is a target of several layers gets the same neighbourhood in each, since draws are keyed by
+ * (seed, source, step)).  Node ids of the batch must lie in [0, n_items). */
+int ps_prepare_plan_online(const int64_t* batch, int64_t B, const ps_graph_t* graph, int64_t n_items, int n_hops,
+                           double alpha, uint64_t seed, int T, int n_layers, int need_backward, void* arena,
+                           int64_t arena_bytes, ps_plan_desc* out, ps_stream_t stream);
 
 /* ---- K13: Adam step on a flat fp32 parameter buffer (torch.optim.Adam defaults:
  *      betas, eps, no weight decay, no amsgrad; pinsage_training.py:147,191).
