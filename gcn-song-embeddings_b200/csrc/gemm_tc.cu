@@ -48,6 +48,9 @@ struct TcArgs {
     const uint8_t* bpack;  // BPACK kernels: hi/lo images of the Q operand, one [2][BN x 128 B] block per (n-tile, k-block)
     uint32_t* mask; int64_t ldm;  // optional sign mask of the activation, one bit per output element (ldm in 32-bit words)
     unsigned long long* dbg;  // development: per-CTA cycle counters of the role waits (ps_gemm_tc_trace), nullptr = off
+    // candidate filter (ps_gemm_filter, packed-weight kernels): no C store; element (i, j) >= filt_thr[j] appends
+    // (value, i) to list j: filt_cnt[j]++ -> slot; filt_val / filt_row [j, slot] when slot < filt_cap
+    const float* filt_thr; int32_t* filt_cnt; float* filt_val; int32_t* filt_row; int filt_cap;
     float* p_colsum;  // weight-gradient kernels (MN-major x MN-major): p_colsum[i] += sum_r P(i, r) -- the bias gradient, from the
                       // elements the producers already hold for the hi/lo split (replaces a separate pass over P)
 };
@@ -651,6 +654,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(TcArgs a) {
             const bool row_ok = row < a.M;
             float* bs = bias_s + tile_par * BN;
             if (a.bias != nullptr && tid < BN) bs[tid] = wk.n0 + tid < a.N ? __ldg(a.bias + wk.n0 + tid) : 0.f;
+            if (BPACK && MASK == 0 && a.filt_thr != nullptr && tid < BN) bs[tid] = wk.n0 + tid < a.N ? __ldg(a.filt_thr + wk.n0 + tid) : INFINITY;
             uint32_t mbits[HALF / 32];
             if (MASK == 2) {
                 const uint32_t* mrow = a.mask + row * a.ldm + col0 / 32;
@@ -677,6 +681,25 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(TcArgs a) {
             // 37-56 % waiting for them to free an accumulator, so this code is kept lean: nothing per element that the
             // call does not ask for, shared-memory accesses as LDS/STS, store mode chosen once per tile.)
             const long long d_e0 = (a.dbg && tid == 0) ? clock64() : 0;
+            if (BPACK && MASK == 0 && a.filt_thr != nullptr) {
+                // kNN candidate filter: nothing is stored but the (few) elements that reach their column's threshold
+                asm volatile("bar.sync 1, 256;" ::: "memory");  // bs holds the thresholds of this tile's columns
+                if (row_ok) {
+                    const float* th = bs + half * HALF;
+#pragma unroll
+                    for (int j = 0; j < HALF; ++j) {
+                        if (acc[j] >= th[j]) {
+                            const int64_t col = col0 + j;
+                            const int slot = atomicAdd(a.filt_cnt + col, 1);
+                            if (slot < a.filt_cap) {
+                                a.filt_val[col * a.filt_cap + slot] = acc[j];
+                                a.filt_row[col * a.filt_cap + slot] = static_cast<int32_t>(row);
+                            }
+                        }
+                    }
+                }
+                continue;
+            }
             if (a.bias != nullptr) {
                 asm volatile("bar.sync 1, 256;" ::: "memory");  // bs was filled before the drain
                 const float4* b4 = reinterpret_cast<const float4*>(bs + half * HALF);
@@ -944,7 +967,8 @@ int ps_gemm_tc_launch(const float* P, int64_t ldp, int p_kmajor, const int32_t* 
     if (!accumulate && K > 4 * kMaxChainK) return PS_ERR_UNSUPPORTED;
     if (accumulate && ps_ceil_div(K, splits < 1 ? 1 : splits) > kMaxChainK) splits = static_cast<int>(ps_ceil_div(K, kMaxChainK));
     const int BN = (N > 128) ? 256 : 128;
-    TcArgs a{P, ldp, p_rows, Q, ldq, q_rows, C, ldc, M, N, K, bias, norm_out, act, l2norm, accumulate, 0, 0, 0, 0, nullptr, mask, ldm, g_tc_dbg, p_colsum};
+    TcArgs a{P, ldp, p_rows, Q, ldq, q_rows, C, ldc, M, N, K, bias, norm_out, act, l2norm, accumulate, 0, 0, 0, 0, nullptr, mask, ldm, g_tc_dbg,
+             nullptr, nullptr, nullptr, nullptr, 0, p_colsum};
     const int64_t num_kb = ps_ceil_div(K, BK);
     if (splits < 1) splits = 1;
     a.kb_per_split = static_cast<int>(ps_ceil_div(num_kb, splits));
@@ -977,4 +1001,27 @@ int ps_gemm_tc_launch(const float* P, int64_t ldp, int p_kmajor, const int32_t* 
     PS_TC_CASE(false, false)
 #undef PS_TC_CASE
     return PS_ERR_UNSUPPORTED;
+}
+
+// kNN candidate filter on the packed-weight kernels: for every (i, j) with sum_r P[i,r] Q[j,r] >= thr[j], append (value, i)
+// to list j.  P [M, K] (the embedding table) streams through the producers, Q [N, K] (the query tile) is the packed
+// "weight" operand; the similarity tile is never written.
+extern "C" int ps_gemm_filter(const float* P, int64_t ldp, const float* Q, int64_t ldq, int64_t M, int64_t N, int64_t K,
+                              const float* thr, int32_t* cnt, float* cand_val, int32_t* cand_row, int cap, ps_stream_t stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    PS_REQUIRE(P && Q && thr && cnt && cand_val && cand_row && cap > 0, "null pointer");
+    if (M < 1024 || N < 64 || K < 32 || K > 8192 || (ldp | ldq | N | K) % 4 != 0 ||
+        (reinterpret_cast<uintptr_t>(P) | reinterpret_cast<uintptr_t>(Q)) % 16 != 0)
+        return ps_fail(PS_ERR_UNSUPPORTED, "ps_gemm_filter: shape outside the packed tensor-core path");
+    const int BN = (N > 128) ? 256 : 128;
+    TcArgs a{P, ldp, nullptr, Q, ldq, nullptr, nullptr, 0, M, N, K, nullptr, nullptr, 0, 0, 0, 0, 0, 0, 0, nullptr, nullptr, 0, g_tc_dbg,
+             thr, cnt, cand_val, cand_row, cap, nullptr};
+    const int64_t num_kb = ps_ceil_div(K, BK);
+    a.kb_per_split = static_cast<int>(num_kb);
+    a.zs = 1;
+    a.mt = ps_ceil_div(M, BM);
+    a.nt = ps_ceil_div(N, BN);
+    const bool pairs = g_tc_cluster && a.mt * a.nt >= 2 * 148;
+    if (pairs) return BN == 256 ? launch_tc<true, true, 256, true, 0, 2>(a, 1, stream) : launch_tc<true, true, 128, true, 0, 2>(a, 1, stream);
+    return BN == 256 ? launch_tc<true, true, 256, true>(a, 1, stream) : launch_tc<true, true, 128, true>(a, 1, stream);
 }

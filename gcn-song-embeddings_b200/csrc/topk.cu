@@ -27,6 +27,7 @@ __device__ __forceinline__ float key_value(uint32_t k) {
 
 __global__ void __launch_bounds__(kThreads)
 topk_rows_kernel(const float* __restrict__ x, int64_t ld, int64_t n_cols, int k, int kp2,
+                 const int32_t* __restrict__ col_ids, const int32_t* __restrict__ row_counts,
                  float* __restrict__ out_val, int64_t* __restrict__ out_idx) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     uint64_t* sel = reinterpret_cast<uint64_t*>(smem_raw);           // [kp2] winners
@@ -35,6 +36,10 @@ topk_rows_kernel(const float* __restrict__ x, int64_t ld, int64_t n_cols, int k,
     __shared__ uint32_t s_prefix, s_need, s_nsel, s_neq;
     const int tid = threadIdx.x;
     const float* row = x + static_cast<int64_t>(blockIdx.x) * ld;
+    // candidate lists (ps_topk_rows_mapped): only the first row_counts[row] entries are valid and entry i stands for
+    // column col_ids[row, i] (ranking on ties and the reported index use that id)
+    const int32_t* ids = col_ids ? col_ids + static_cast<int64_t>(blockIdx.x) * ld : nullptr;
+    if (row_counts != nullptr) n_cols = min(n_cols, static_cast<int64_t>(max(__ldg(row_counts + blockIdx.x), 0)));
     const bool vec = (ld % 4 == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0);
     const int64_t n4 = vec ? n_cols / 4 : 0;
 
@@ -88,6 +93,7 @@ topk_rows_kernel(const float* __restrict__ x, int64_t ld, int64_t n_cols, int k,
     // ---- collect: everything above the threshold, and the columns that equal it
     auto take = [&](float v, int64_t col) {
         const uint32_t key = order_key(v);
+        if (ids != nullptr) col = __ldg(ids + col);
         if (key > thr) {
             const uint32_t p = atomicAdd(&s_nsel, 1u);
             sel[p] = (static_cast<uint64_t>(key) << 32) | (0xFFFFFFFFu - static_cast<uint32_t>(col));
@@ -149,7 +155,25 @@ extern "C" int ps_topk_rows(const float* x, int64_t ld, int64_t n_rows, int64_t 
     const size_t smem = static_cast<size_t>(kp2) * 8 + kEqCap * 4 + 4096 * 4;
     if (smem > 48 * 1024)
         PS_CUDA_CHECK(cudaFuncSetAttribute(topk_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-    topk_rows_kernel<<<static_cast<unsigned>(n_rows), kThreads, smem, stream>>>(x, ld, n_cols, k, kp2, out_val, out_idx);
+    topk_rows_kernel<<<static_cast<unsigned>(n_rows), kThreads, smem, stream>>>(x, ld, n_cols, k, kp2, nullptr, nullptr, out_val, out_idx);
+    PS_LAUNCH_CHECK();
+    return PS_OK;
+}
+
+// The same selection over per-row candidate lists (the output of ps_gemm_filter): row r holds row_counts[r] valid
+// (value, column id) pairs; rows with fewer than k candidates are padded with (-inf, -1).
+extern "C" int ps_topk_rows_mapped(const float* x, const int32_t* col_ids, const int32_t* row_counts, int64_t ld,
+                                   int64_t n_rows, int k, float* out_val, int64_t* out_idx, ps_stream_t stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    PS_REQUIRE(x && col_ids && row_counts && out_val && out_idx, "null pointer");
+    PS_REQUIRE(k > 0 && k <= 8192 && k <= ld, "k must be in [1, min(8192, ld)] (got %d)", k);
+    if (n_rows == 0) return PS_OK;
+    int kp2 = 32;
+    while (kp2 < k) kp2 <<= 1;
+    const size_t smem = static_cast<size_t>(kp2) * 8 + kEqCap * 4 + 4096 * 4;
+    if (smem > 48 * 1024)
+        PS_CUDA_CHECK(cudaFuncSetAttribute(topk_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    topk_rows_kernel<<<static_cast<unsigned>(n_rows), kThreads, smem, stream>>>(x, ld, ld, k, kp2, col_ids, row_counts, out_val, out_idx);
     PS_LAUNCH_CHECK();
     return PS_OK;
 }

@@ -18,7 +18,7 @@ os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
 import torch  # noqa: E402
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libpinsage_b200.so")
+LIB_PATH = os.environ.get("PS_LIB_PATH") or os.path.join(_HERE, "libpinsage_b200.so")  # PS_LIB_PATH: development builds
 
 _lib = None
 _tls = threading.local()  # the library's CUDA runtime keeps a current device per host thread
@@ -46,6 +46,7 @@ _SIGNATURES = {
     "ps_graph_create": ([c_void_p, c_void_p, c_int64, c_int64, c_int64, ctypes.POINTER(c_void_p), c_void_p], c_int),
     "ps_graph_destroy": ([c_void_p], c_int),
     "ps_graph_use_indptr32": ([c_void_p, c_int], c_int),
+    "ps_walk_algo": ([c_int], c_int),
     "ps_walk_topt": ([c_void_p, c_void_p, c_int64, c_int, c_double, c_int, c_int, c_uint64,
                       c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p], c_int),
     "ps_trace_topt": ([c_void_p, c_void_p, c_int64, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p], c_int),
@@ -120,6 +121,8 @@ _SIGNATURES.update({
     "ps_train_step": ([ctypes.POINTER(StepArgsC), c_void_p], c_int),
     "ps_profile_enable": ([c_int], c_int),
     "ps_profile_dump": ([c_char_p, c_int64], c_int64),
+    "ps_gemm_filter": ([c_void_p, c_int64, c_void_p, c_int64, c_int64, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p], c_int),
+    "ps_topk_rows_mapped": ([c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int, c_void_p, c_void_p, c_void_p], c_int),
     "ps_csr_build": ([c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_void_p], c_int),
     "ps_standardize": ([c_void_p, c_int64, c_int64, c_int, c_double, c_void_p, c_void_p, c_void_p], c_int),
 })
@@ -324,6 +327,11 @@ class GraphHandle:
         h, self._h = getattr(self, "_h", None), None
         if h and _lib is not None:
             _lib.ps_graph_destroy(h)
+
+
+def walk_algo(mode: int) -> int:
+    """0 = sort-based walker kernel where it applies (default), 1 = hash-table kernel always; returns the previous mode."""
+    return lib().ps_walk_algo(int(mode))
 
 
 def walk_topt(graph: GraphHandle, sources: torch.Tensor, n_hops: int, alpha: float, T: int, seed: int,
@@ -543,6 +551,31 @@ def topk_rows(x, k):
     idx = torch.empty((n, k), dtype=torch.int64, device="cuda")
     check(lib().ps_topk_rows(_p(x, torch.float32), _ld(x), int(n), int(m), int(k), _p(val), _p(idx), _stream()))
     return val, idx
+
+
+def gemm_filter(table, queries, thr, cap):
+    """ps_gemm_filter: candidate lists (cnt int32 [nq], val float32 [nq, cap], row int32 [nq, cap]) of the table rows
+    whose dot product with query j reaches thr[j].  Raises NativeError(-4) for shapes outside the packed path."""
+    _ensure_device()
+    nq, d = queries.shape
+    cnt = torch.zeros(nq, dtype=torch.int32, device="cuda")
+    val = torch.empty((nq, cap), dtype=torch.float32, device="cuda")
+    row = torch.empty((nq, cap), dtype=torch.int32, device="cuda")
+    with _Timed("gemm_knn_filter", 2.0 * table.shape[0] * nq * d, 4.0 * (table.numel() + queries.numel())):
+        check(lib().ps_gemm_filter(_p(table, torch.float32), _ld(table), _p(queries, torch.float32), _ld(queries), int(table.shape[0]),
+                                   int(nq), int(d), _p(thr, torch.float32), _p(cnt), _p(val), _p(row), int(cap), _stream()))
+    return cnt, val, row
+
+
+def topk_rows_mapped(val, col_ids, counts, k):
+    """ps_topk_rows_mapped: exact top-k of per-row candidate lists -> (values [n, k], original column ids int64 [n, k])."""
+    _ensure_device()
+    n, cap = val.shape
+    out_v = torch.empty((n, k), dtype=torch.float32, device="cuda")
+    out_i = torch.empty((n, k), dtype=torch.int64, device="cuda")
+    check(lib().ps_topk_rows_mapped(_p(val, torch.float32), _p(col_ids, torch.int32), _p(counts, torch.int32), int(cap), int(n), int(k),
+                                    _p(out_v), _p(out_i), _stream()))
+    return out_v, out_i
 
 
 def csr_build(src, dst, n_nodes):

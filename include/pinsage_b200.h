@@ -63,6 +63,10 @@ int ps_walk_topt(const ps_graph_t* g, const int64_t* sources, int64_t n, int n_h
                  int fixed_len, int T, uint64_t seed,
                  int64_t* out_nodes_i64, double* out_w_f64, int32_t* out_nodes_i32, float* out_w_f32,
                  int32_t* out_trace, ps_stream_t stream);
+/* Two kernels implement ps_walk_topt / ps_trace_topt with identical results: the sort-based one (trace in shared memory,
+ * sorted in registers; n_hops <= 512 and T <= 256) and the hash-table one (everything else).  mode = 1 forces the
+ * hash-table kernel (parity tests of that path), 0 restores the default; returns the previous mode. */
+int ps_walk_algo(int mode);
 /* K2 alone on a caller-supplied trace [n, n_hops] (bit-exact parity hook against
  * sample_neighborhood_topt fed the same trace, pinsage_model.py:96-99,107). */
 int ps_trace_topt(const int64_t* trace, const int64_t* sources, int64_t n, int n_hops, int T,
@@ -215,6 +219,19 @@ int ps_sample_batch(const int64_t* positives, int64_t P, const int64_t* all_ids,
  *      column; NaN sorts as the largest value (as torch.topk).  1 <= k <= min(8192, n_cols), n_cols < 2^32. ---- */
 int ps_topk_rows(const float* x, int64_t ld, int64_t n_rows, int64_t n_cols, int k,
                  float* out_val, int64_t* out_idx, ps_stream_t stream);
+/* The fused form of the kNN search (baselines.py:91-103 without the [queries, N] similarity
+ * tile): ps_gemm_filter runs the similarity GEMM sim[i, j] = sum_r P[i,r] Q[j,r] (P = the embedding table [M, K],
+ * Q = a tile of query rows [N, K], both K-major, tcgen05 packed-weight path) and, instead of storing sim, appends
+ * (sim, i) to query j's candidate list when sim >= thr[j]: slot = cnt[j]++ (cnt zeroed by the caller), written when
+ * slot < cap to cand_val / cand_row [j * cap + slot].  The caller derives thr[j] from a sample of the table so that
+ * a list ends up with a small multiple of k entries, checks cnt afterwards (cnt[j] < k or > cap: widen and redo),
+ * and finishes with ps_topk_rows_mapped: the exact top-k of every list, ties by ascending row id like ps_topk_rows.
+ * Returns PS_ERR_UNSUPPORTED for shapes outside the packed path (M < 1024, N < 64, K < 32, K % 4). */
+int ps_gemm_filter(const float* P, int64_t ldp, const float* Q, int64_t ldq, int64_t M, int64_t N, int64_t K,
+                   const float* thr, int32_t* cnt, float* cand_val, int32_t* cand_row, int cap, ps_stream_t stream);
+int ps_topk_rows_mapped(const float* x, const int32_t* col_ids, const int32_t* row_counts, int64_t ld,
+                        int64_t n_rows, int k, float* out_val, int64_t* out_idx, ps_stream_t stream);
+
 
 /* ---- weight + bias gradient of a Linear layer in one call (AddmmBackward of nn.Linear, pinsage_model.py:201,208,259):
  *      C[i,j] += sum_r P[r*ldp + i] * Q[rows(r)*ldq + j]   (dW += dY^T X, optional row gather on X)

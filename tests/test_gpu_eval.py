@@ -181,3 +181,57 @@ def test_topk_rows_matches_torch(n_rows, n_cols, k):
     big = torch.randn(n_rows, n_cols + 12, device="cuda")
     v2, i2 = nat.topk_rows(big[:, :n_cols], k)
     assert torch.equal(v2, big[:, :n_cols].topk(k, dim=1).values)
+
+@pytest.mark.parametrize("n,d,k,nq", [(60_000, 128, 500, 700), (200_000, 64, 1000, 1024), (30_000, 32, 300, 130)])
+def test_knn_fused_matches_tile_path(n, d, k, nq):
+    """The fused search (ps_gemm_filter: candidates above a sampled per-query threshold, then the exact top-(k+1) of
+    the short lists; no [queries, N] tile) returns what the tile + ps_topk_rows path returns, and both match an fp64
+    restatement of baselines.knn_from_emb (baselines.py:91-103).  Duplicate rows make exact ties (ranked by row id)."""
+    import ps_knn
+    gen = torch.Generator(device="cuda").manual_seed(n + k)
+    emb = torch.randn((n, d), generator=gen, device="cuda") + 0.5
+    emb[n // 2: n // 2 + 40] = emb[:40]  # exact duplicates: ties between a row and its copy
+    q = torch.randint(0, n, (nq,), generator=gen, device="cuda")
+    q[:20] = torch.arange(20, device="cuda")
+    ps_knn.fused_stats.update(tiles=0, fallback_tiles=0)
+    w_f, n_f = ps_knn.knn_from_emb(emb, q, k, q_tile=512)
+    assert ps_knn.fused_stats["tiles"] > 0 and ps_knn.fused_stats["fallback_tiles"] == 0, ps_knn.fused_stats
+    w_t, n_t = ps_knn.knn_from_emb(emb, q, k, q_tile=512, fused=False)
+    e64 = emb.double() / emb.double().norm(dim=1, keepdim=True)
+    for lo in range(0, nq, 256):
+        sim = e64[q[lo:lo + 256]] @ e64.T
+        ref_w, ref_n = sim.topk(k + 1, dim=1)
+        ref_w = ref_w[:, 1:]
+        for w, nb in ((w_f, n_f), (w_t, n_t)):
+            assert torch.allclose(w[lo:lo + 256].double(), ref_w, rtol=0, atol=2e-6)
+            got = torch.gather(sim, 1, nb[lo:lo + 256])  # the returned ids really carry the returned similarities
+            assert torch.allclose(got, w[lo:lo + 256].double(), rtol=0, atol=2e-6)
+    # the two paths order ties the same way (value desc, row id asc); rounding of the two GEMM orientations may differ
+    # in the last bit, so ids are compared where neighbouring similarities are separated
+    gap = (w_t[:, :-1] - w_t[:, 1:]).abs()
+    sep = torch.ones_like(w_t, dtype=torch.bool)
+    sep[:, :-1] &= gap > 1e-6
+    sep[:, 1:] &= gap > 1e-6
+    assert (n_f[sep] == n_t[sep]).all()
+    assert (n_f == n_t).float().mean() > 0.999
+
+
+def test_knn_fused_falls_back_when_threshold_misses(monkeypatch):
+    """A threshold that admits too few candidates is detected (list shorter than k + 1) and the tile is redone
+    through the tile path: the result stays exact."""
+    import ps_knn
+    torch.manual_seed(5)
+    emb = torch.randn(40_000, 64, device="cuda")
+    q = torch.arange(256, device="cuda")
+    ref = ps_knn.knn_from_emb(emb, q, 400, fused=False)
+    real = ps_knn.nat.topk_rows
+
+    def too_high(x, kk):  # the sample tile is the only call with fewer than N columns: push its thresholds above 1
+        v, i = real(x, kk)
+        return (v + 1.0, i) if x.shape[1] < emb.shape[0] else (v, i)
+
+    monkeypatch.setattr(ps_knn.nat, "topk_rows", too_high)
+    ps_knn.fused_stats.update(tiles=0, fallback_tiles=0)
+    got = ps_knn.knn_from_emb(emb, q, 400)
+    assert ps_knn.fused_stats["fallback_tiles"] == ps_knn.fused_stats["tiles"] > 0
+    assert torch.equal(got[1], ref[1]) and torch.equal(got[0], ref[0])

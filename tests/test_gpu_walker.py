@@ -14,6 +14,15 @@ def nat():
     return ps_native
 
 
+@pytest.fixture(params=[0, 1], ids=["sort_kernel", "hash_kernel"], autouse=True)
+def walk_algo(request, nat):
+    """Every test of this module runs on both implementations of ps_walk_topt / ps_trace_topt (ps_walk_algo): the
+    sort-based kernel (n_hops <= 512, T <= 256) and the hash-table kernel (forced; it also takes the larger shapes)."""
+    old = nat.walk_algo(request.param)
+    yield request.param
+    nat.walk_algo(old)
+
+
 def _graph(nat, indptr, indices, n_tracks):
     n_cols = len(indptr) - 1 - n_tracks
     return nat.GraphHandle(torch.from_numpy(np.asarray(indptr)), torch.from_numpy(np.asarray(indices)), n_tracks, n_cols)
@@ -36,7 +45,9 @@ def test_trace_topt_matches_reference(nat, golden, tag, T):
 
 
 @pytest.mark.parametrize("n_hops,alpha,fixed_len,T", [(500, 0.85, 0, 100), (37, 0.5, 0, 5), (1000, 0.85, 0, 50),
-                                                      (64, 0.0, 0, 10), (96, 1.0, 0, 10), (400, 0.85, 4, 50), (15, 0.85, 5, 3)])
+                                                      (64, 0.0, 0, 10), (96, 1.0, 0, 10), (400, 0.85, 4, 50), (15, 0.85, 5, 3),
+                                                      (500, 0.85, 0, 3), (512, 0.3, 0, 17), (256, 0.85, 0, 200), (129, 0.6, 0, 256),
+                                                      (300, 0.85, 3, 50)])
 def test_walker_bit_exact_vs_oracle(nat, golden, n_hops, alpha, fixed_len, T):
     """K1: the Philox walker's traces equal the CPU restatement's bit for bit, for any
     launch shape, and the fused top-T equals the oracle's reduction of that trace."""

@@ -30,4 +30,12 @@ for pack in (1, 0):
     print(f"N={args.n}: similarity GEMM [1024 x N x 128], weight packing {pack}: {timed(lambda: nat.gemm(qe, en, out, 1024, args.n, 128)):.2f} ms")
 nat.gemm_tc_pack(1)
 print(f"  ps_topk_rows {timed(lambda: nat.topk_rows(sim, args.k + 1)):.2f} ms   torch.topk {timed(lambda: sim.topk(args.k + 1, dim=1)):.2f} ms")
-print(f"  knn_from_emb end to end {timed(lambda: ps_knn.knn_from_emb(emb, q, args.k)):.2f} ms per 1024 queries")
+print(f"  knn_from_emb (tile + ps_topk_rows) {timed(lambda: ps_knn.knn_from_emb(emb, q, args.k, fused=False)):.2f} ms per 1024 queries")
+ps_knn.fused_stats.update(tiles=0, fallback_tiles=0)
+print(f"  knn_from_emb (fused: sample -> ps_gemm_filter -> ps_topk_rows_mapped) {timed(lambda: ps_knn.knn_from_emb(emb, q, args.k)):.2f} ms per 1024 queries   {ps_knn.fused_stats}")
+k1 = args.k + 1
+thr = nat.topk_rows(sim[:, ::17].contiguous()[:, : (sim[:, ::17].shape[1] // 4) * 4], 128)[0][:, -1].contiguous()
+cap = 4660
+print(f"  ps_gemm_filter alone {timed(lambda: nat.gemm_filter(en, qe, thr, cap)):.2f} ms")
+cnt, val, row = nat.gemm_filter(en, qe, thr, cap)
+print(f"  candidates per query: min {int(cnt.min())} mean {float(cnt.float().mean()):.0f} max {int(cnt.max())};  ps_topk_rows_mapped {timed(lambda: nat.topk_rows_mapped(val, row, cnt, k1)):.3f} ms")
