@@ -150,6 +150,31 @@ def measured_traffic(tag):
         return json.load(f).get("dram_bytes_per_launch", {}).get(tag)
 
 
+def walk_roofline(n_sources, n_hops, ms, peaks):
+    """The walker against its bounds: algorithmic bytes (28 B per step), the DRAM bytes one launch
+    really moves (ncu capture named in profiles/traffic.json, scaled by the number of steps), and the DRAM
+    RANDOM-ACCESS ceiling measured with tools/random_access_bench.cu: every step ends in a 4-byte read at a random
+    place of a CSR that is far larger than L2, which costs a full 64-byte burst, and the memory system serves a fixed
+    number of such bursts per second whatever the kernel does."""
+    steps = n_sources * n_hops
+    out = {"algorithmic_gbs": round(steps * 28 / ms / 1e6, 2), "frac_of_hbm": round(steps * 28 / ms / 1e6 / peaks["hbm_gbs"], 4)}
+    path = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.isfile(path):
+        with open(path) as f:
+            t = json.load(f)
+        per_step = t.get("walk_dram_bytes_per_step")
+        rate = t.get("random_access_gacc_per_s_320MB_table")
+        if per_step:
+            out["traffic"] = round(per_step * steps)
+            out["dram_gbs"] = round(per_step * steps / ms / 1e6, 1)
+            out["frac_of_hbm_dram_measured"] = round(per_step * steps / ms / 1e6 / peaks["hbm_gbs"], 4)
+            if rate:
+                bound_ms = per_step * steps / 64.0 / (rate * 1e9) * 1e3
+                out["random_access_bound"] = {"bursts_per_step": round(per_step / 64.0, 3), "gacc_per_s": rate, "bound_ms": round(bound_ms, 2),
+                                              "frac_of_bound": round(bound_ms / ms, 3), "source": t.get("random_access_source")}
+    return out
+
+
 def roofline_from_profile(summary, steps, peaks):
     """Pick the kernel with the largest share of the step and report it against its bound."""
     if not summary:
@@ -666,8 +691,7 @@ def run_ours(args, wl):
             "gpu_launches": launches, "clocks": clocks,
             "walk": {"metric": "walk_steps_per_sec", "value": round(walk_steps_per_s, 1), "unit": "steps/s",
                      "sources": N, "n_hops": 500, "alpha": 0.85, "T": 100, "ms": round(walk_ms, 3),
-                     "algorithmic_gbs": round(walk_steps_per_s * 28 / 1e9, 2),
-                     "frac_of_hbm": round(walk_steps_per_s * 28 / 1e9 / peaks["hbm_gbs"], 4)},
+                     **walk_roofline(N, 500, walk_ms, peaks)},
             "final_loss": final_loss, "host_ms_per_step": host_ms, "cudaMallocs_in_timed_region": dev_allocs,
             "host_placement": numa_note}
     import ps_engine
