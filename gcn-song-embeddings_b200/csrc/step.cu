@@ -264,6 +264,8 @@ extern "C" int ps_train_step(const ps_step_args* a, ps_stream_t stream_) {
             PS_TRY(ps_scatter_add_rows(lb.d_self, din, lp.self_rows, lb.d_h_in, din, lp.n, din, stream));
             d_h = lb.d_h_in;
         }
+        if (l == 1 && a->upper_grads_event != nullptr)  // everything but layer 0's gradients is final from here on
+            PS_CUDA_CHECK(cudaEventRecord(static_cast<cudaEvent_t>(a->upper_grads_event), stream));
     }
     if (a->emb_out != nullptr) *a->emb_out = b.out;
     return PS_OK;

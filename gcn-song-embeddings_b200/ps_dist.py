@@ -72,6 +72,40 @@ def allreduce_mean_(flat: torch.Tensor, world_size: int):
     return flat
 
 
+class GradSync:
+    """The per-step gradient exchange of one replica.  The flat gradient is summed over the ranks in two parts: the
+    layers above layer 0 and the head are final about half way through the backward (ps_train_step records an event
+    there), so their allreduce runs on NCCL's stream while layer 0's backward -- the bulk of the step -- still computes;
+    only layer 0's own gradients (conv_layers.0.*, the first parameters of the flat buffer) are exchanged after the
+    last kernel.  The mean's 1 / world_size is folded into the Adam kernel (FlatAdam.grad_scale)."""
+
+    def __init__(self, trainer, world_size):
+        self.engine, self.world = trainer.model.engine, world_size
+        self.engine.want_upper_grads_event = True
+        opt = trainer.optimizer
+        self.scale_in_optimizer = hasattr(opt, "grad_scale")
+        if self.scale_in_optimizer:
+            opt.grad_scale = 1.0 / world_size
+        self.comm = None
+
+    def __call__(self):
+        eng, flat = self.engine, self.engine.flat_grad
+        ev, off = getattr(eng, "upper_grads_event", None), getattr(eng, "upper_grads_offset", 0)
+        if ev is not None and 0 < off < flat.numel():
+            if self.comm is None:
+                self.comm = torch.cuda.Stream(priority=-1)
+            self.comm.wait_event(ev)
+            with torch.cuda.stream(self.comm):
+                early = dist.all_reduce(flat[off:], op=dist.ReduceOp.SUM, async_op=True)
+            dist.all_reduce(flat[:off], op=dist.ReduceOp.SUM)
+            early.wait()  # the current stream waits for the early part
+            eng.upper_grads_event = None
+        else:
+            dist.all_reduce(flat, op=dist.ReduceOp.SUM)
+        if not self.scale_in_optimizer:
+            flat.div_(self.world)
+
+
 def broadcast_parameters(model, src=0):
     """Make every rank start from rank `src`'s parameters."""
     if dist.is_initialized() and dist.get_world_size() > 1:
@@ -99,8 +133,7 @@ def attach(trainer, rank: int, world_size: int):
     seed_rank_streams(rank, world_size)
     if world_size > 1:
         broadcast_parameters(trainer.model)
-        engine = trainer.model.engine
-        trainer._grad_sync = lambda: allreduce_mean_(engine.flat_grad, world_size)
+        trainer._grad_sync = GradSync(trainer, world_size)
     return trainer
 
 

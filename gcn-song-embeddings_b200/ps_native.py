@@ -98,7 +98,8 @@ class StepArgsC(ctypes.Structure):
                 ("margin", c_float), ("feat_margin", c_float),
                 ("flat_grad", c_void_p), ("n_params", c_int64),
                 ("workspace", c_void_p), ("workspace_bytes", c_int64),
-                ("loss_out", c_void_p), ("batch", c_void_p), ("diag_out", c_void_p), ("emb_out", ctypes.POINTER(c_void_p))]
+                ("loss_out", c_void_p), ("batch", c_void_p), ("diag_out", c_void_p), ("emb_out", ctypes.POINTER(c_void_p)),
+                ("upper_grads_event", c_void_p)]
 
 
 class PlanDescLayerC(ctypes.Structure):
