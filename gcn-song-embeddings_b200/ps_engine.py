@@ -319,6 +319,9 @@ class Engine:
         for l, lp in enumerate(plan.layers):
             conv = m.conv_layers[l]
             din = in_dims[l]
+            if not keep and do <= 128 and do < dh:
+                h_prev = self._conv_projected(h_prev, din, lp.nz, lp.zrows, lp.n, lp.self_rows, lp.nbz, lp.w, conv, l)
+                continue
             z = torch.empty((lp.nz, dh), dtype=torch.float32, device="cuda")
             # training: the GEMM also records sign(z) (1 bit per element) so the backward never re-reads z for leaky'
             zmask = None
@@ -345,6 +348,44 @@ class Engine:
         nat.gemm(a1, m.G2.weight, out, n_top, do, do)
         ctx = (plan, saved, a1) if keep else None
         return out, ctx
+
+    # ---- inference form of a layer: aggregate AFTER the W projection ------------------------------------------
+    def _projected_rows(self, h_in, din, nz, zrows, conv, l, row_block=1 << 21):
+        """zp [nz, do] = leaky(Q x + b) . W[:, din:]^T for the nz needed input rows, in row blocks so that the dh-wide z
+        (2 KB per row at dh = 512: 41 GB for 20 M rows) is never materialised as a whole."""
+        _, dh, do = self._dims()
+        w2 = conv.W.weight.detach()[:, din:]  # [do, dh] view, leading dimension din + dh
+        zp = torch.empty((nz, do), dtype=torch.float32, device="cuda")
+        for b0 in range(0, nz, row_block):
+            nb = min(row_block, nz - b0)
+            z = torch.empty((nb, dh), dtype=torch.float32, device="cuda")
+            rows = zrows[b0:b0 + nb] if zrows is not None else None
+            src = h_in if zrows is not None else h_in[b0:b0 + nb]
+            nat.gemm(src, conv.Q.weight, z, nb, dh, din, p_rows=rows, bias=conv.Q.bias, act=1, tag=f"gemm_q_fwd_l{l}")
+            nat.gemm(z, w2, zp[b0:b0 + nb], nb, do, dh, tag=f"gemm_proj_fwd_l{l}")
+            del z
+        return zp
+
+    def _projected_weight(self, conv, din):
+        """[W[:, :din] | I]: the weight that turns cat' = [x_self | aggregated projections] into W x_cat of the reference
+        layer (the identity block multiplies exactly under the hi/lo split: hi(1) = 1, lo(1) = 0)."""
+        _, _, do = self._dims()
+        w = conv.W.weight.detach()
+        return torch.cat([w[:, :din], torch.eye(do, dtype=torch.float32, device=w.device)], dim=1).contiguous()
+
+    def _conv_projected(self, h_in, din, nz, zrows, n, self_rows, nbz, w, conv, l):
+        """One ConvLayer without a backward (pinsage_model.py:189-212), with the importance-weighted mean taken AFTER the
+        neighbour part of the W projection: W [x | mean_t z_t] = W1 x + mean_t (W2 z_t).  The gathered rows are do wide
+        instead of dh wide (4x fewer bytes at 512 / 128, and the aggregation is the HBM-bound part of inference); per
+        row the result differs from the training-form layer by fp32 summation order only (~1e-7)."""
+        _, dh, do = self._dims()
+        zp = self._projected_rows(h_in, din, nz, zrows, conv, l)
+        cat = torch.empty((n, din + do), dtype=torch.float32, device="cuda")
+        inv_wsum = torch.empty((n,), dtype=torch.float32, device="cuda")
+        nat.aggregate_fwd(h_in, self_rows, din, zp, nbz, w, do, cat, inv_wsum, tag=f"aggregate_fwd_l{l}")
+        h = torch.empty((n, do), dtype=torch.float32, device="cuda")
+        nat.gemm(cat, self._projected_weight(conv, din), h, n, do, din + do, bias=conv.W.bias, act=1, l2norm=True, tag=f"gemm_w_fwd_l{l}")
+        return h
 
     # ---- backward --------------------------------------------------------------------
     def backward(self, ctx, d_out: torch.Tensor, grads: dict):
@@ -616,8 +657,14 @@ class Engine:
             zpos = (torch.cumsum(zmask, 0, dtype=torch.int32) - 1)
             del zmask
             nz = zrows.numel()
-            z = torch.empty((nz, dh), dtype=torch.float32, device=dev)
-            nat.gemm(h_prev, conv.Q.weight, z, nz, dh, din, p_rows=zrows, bias=conv.Q.bias, act=1, tag=f"gemm_q_fwd_l{l}")
+            projected = do <= 128 and do < dh  # aggregate do-wide projections instead of dh-wide activations (_conv_projected)
+            if projected:
+                z = self._projected_rows(h_prev, din, nz, zrows, conv, l)
+                zw, w_cat = do, self._projected_weight(conv, din)
+            else:
+                z = torch.empty((nz, dh), dtype=torch.float32, device=dev)
+                nat.gemm(h_prev, conv.Q.weight, z, nz, dh, din, p_rows=zrows, bias=conv.Q.bias, act=1, tag=f"gemm_q_fwd_l{l}")
+                zw, w_cat = dh, conv.W.weight
             last = l == L - 1
             h = torch.empty((hi - lo, do) if last else (N, do), dtype=torch.float32, device=dev)
             for i in range(0, targets.numel(), chunk):
@@ -625,14 +672,14 @@ class Engine:
                 n = c.numel()
                 nbz = zpos[table.nodes[c, :T].reshape(-1).long()].view(n, T).contiguous()
                 w = table.w[c, :T].contiguous()
-                cat = torch.empty((n, din + dh), dtype=torch.float32, device=dev)
+                cat = torch.empty((n, din + zw), dtype=torch.float32, device=dev)
                 inv = torch.empty((n,), dtype=torch.float32, device=dev)
-                nat.aggregate_fwd(h_prev, c.to(torch.int32), din, z, nbz, w, dh, cat, inv, tag=f"aggregate_fwd_l{l}")
+                nat.aggregate_fwd(h_prev, c.to(torch.int32), din, z, nbz, w, zw, cat, inv, tag=f"aggregate_fwd_l{l}")
                 out = torch.empty((n, do), dtype=torch.float32, device=dev)
                 if do <= 128:
-                    nat.gemm(cat, conv.W.weight, out, n, do, din + dh, bias=conv.W.bias, act=1, l2norm=True, tag=f"gemm_w_fwd_l{l}")
+                    nat.gemm(cat, w_cat, out, n, do, din + zw, bias=conv.W.bias, act=1, l2norm=True, tag=f"gemm_w_fwd_l{l}")
                 else:
-                    nat.gemm(cat, conv.W.weight, out, n, do, din + dh, bias=conv.W.bias, act=1)
+                    nat.gemm(cat, w_cat, out, n, do, din + zw, bias=conv.W.bias, act=1)
                     nat.l2norm_rows(out, torch.empty((n,), dtype=torch.float32, device=dev))
                 if last:
                     h[c - lo] = out
