@@ -760,6 +760,22 @@ def run_inference(args, wl):
         checksum = float(emb.double().sum())
         del emb
     ms = ps_dist.max_over_ranks(sum(times) / len(times))
+    # one more (untimed) pass with CUDA events around every ABI call: where the pass goes, and the HBM-bound part against its roofline
+    peaks = load_peaks()
+    ps_native.profiler = ps_native.Profiler()
+    ps_dist.embed_shard(tr, chunk=1 << 18, exchange=args.exchange)
+    prof = ps_native.profiler.summary()
+    ps_native.profiler = None
+    kernels = {k: {"ms": round(v["ms"], 2), "launches": v["launches"], "tflops": round(v["flops"] / v["ms"] / 1e9, 1) if v["ms"] else 0.0,
+                   "gbs": round(v["bytes"] / v["ms"] / 1e6, 1) if v["ms"] else 0.0} for k, v in sorted(prof.items(), key=lambda kv: -kv[1]["ms"])}
+    agg = {k: v for k, v in prof.items() if k.startswith("aggregate_fwd")}
+    roofline = None
+    if agg:
+        a_ms, a_bytes = sum(v["ms"] for v in agg.values()), sum(v["bytes"] for v in agg.values())
+        roofline = {"kernel": "aggregate_fwd (all layers)", "bound": "hbm", "achieved": round(a_bytes / a_ms / 1e6, 1), "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                    "frac": round(a_bytes / a_ms / 1e6 / peaks["hbm_gbs"], 4), "traffic": None, "peak_source": peaks["source"],
+                    "ms_per_pass": round(a_ms, 2), "share_of_kernel_time": round(a_ms / max(sum(v["ms"] for v in prof.values()), 1e-9), 3),
+                    "note": "algorithmic bytes: T gathered projection rows (out_dim wide) + the self row + indices / weights + the concatenated row written, per target"}
     if rank == 0:
         print(json.dumps({"metric": "pinsage_embed_nodes_per_sec", "value": round(N / (ms * 1e-3), 1), "unit": "nodes/s", "n_gpus": world,
                           "steps": args.steps, "warmup": args.warmup, "ms_per_pass": round(ms, 2), "higher_is_better": True, "scaling": "strong",
@@ -768,7 +784,11 @@ def run_inference(args, wl):
                                                  f"node-range shards over {world} GPU(s), " + ("layer outputs all-gathered (NCCL)" if args.exchange and world > 1 else "no communication"), "rank0_rows": hi - lo, "rank0_closure": stats},
                           "walk": {"steps_per_s": round(N * 500 / (walk_ms * 1e-3), 1), "ms": round(walk_ms, 2), "sources": N, "n_hops": 500, "T": T},
                           "setup_s": round(setup_s, 1), "hbm_gb_allocated": round(torch.cuda.max_memory_allocated() / 1e9, 1),
-                          "checksum_rank0": checksum}), flush=True)
+                          "checksum_rank0": checksum, "roofline": roofline, "kernels_rank0": kernels,
+                          "cpu_baseline": None if N > 2_000_000 else "see the train mode's line",
+                          "cpu_baseline_note": "the reference's PinSage.embed clones three [N, Din] tables per call (pinsage_training.py:258-275 -> "
+                                               "pinsage_model.py:21-30): 3 x 41 GB at this size, not runnable on the box's host; the CPU port is timed "
+                                               "on the train step (cfg3) instead"}), flush=True)
     ps_dist.barrier()
     ps_dist.shutdown()
     return 0

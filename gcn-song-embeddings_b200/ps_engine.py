@@ -640,23 +640,37 @@ class Engine:
         top[lo:hi] = True
         need[L - 1] = top
         for l in range(L - 1, 0, -1):
-            if gather_layer is not None:
-                need[l - 1] = top  # owners compute, the exchange delivers the rest
+            if gather_layer is not None or (lo == 0 and hi == N):
+                need[l - 1] = top  # owners compute and the exchange delivers the rest / the shard is the whole graph
                 continue
             nxt = need[l].clone()
             mark_neighbours(nxt, need[l].nonzero().squeeze(1))
             need[l - 1] = nxt
         h_prev = feats
+        full_T = T == table.Tp  # table rows are exactly the T neighbours: row slices are views
         for l in range(L):
             conv = m.conv_layers[l]
             din = in_dims[l]
-            targets = need[l].nonzero().squeeze(1)
-            zmask = torch.zeros(N, dtype=torch.bool, device=dev)
-            mark_neighbours(zmask, targets)
-            zrows = zmask.nonzero().squeeze(1).to(torch.int32)
-            zpos = (torch.cumsum(zmask, 0, dtype=torch.int32) - 1)
-            del zmask
-            nz = zrows.numel()
+            # targets: a contiguous range when the mask is the shard itself (top layer; every layer with an exchange or on one
+            # GPU), else the set bits of the closure mask
+            if need[l] is top:
+                t_lo, t_hi, targets = lo, hi, None
+                n_t = hi - lo
+            else:
+                targets = need[l].nonzero().squeeze(1)
+                n_t = targets.numel()
+            # rows that get the Q transform: when the targets reference (nearly) every row anyway -- 3+ references per
+            # row on average -- all N rows are transformed in node order: no mask, no position map, no gather in the GEMM
+            dense_z = n_t * T >= 3 * N
+            if dense_z:
+                zrows, zpos, nz = None, None, N
+            else:
+                zmask = torch.zeros(N, dtype=torch.bool, device=dev)
+                mark_neighbours(zmask, targets if targets is not None else torch.arange(t_lo, t_hi, device=dev))
+                zrows = zmask.nonzero().squeeze(1).to(torch.int32)
+                zpos = (torch.cumsum(zmask, 0, dtype=torch.int32) - 1)
+                del zmask
+                nz = zrows.numel()
             projected = do <= 128 and do < dh  # aggregate do-wide projections instead of dh-wide activations (_conv_projected)
             if projected:
                 z = self._projected_rows(h_prev, din, nz, zrows, conv, l)
@@ -667,26 +681,38 @@ class Engine:
                 zw, w_cat = dh, conv.W.weight
             last = l == L - 1
             h = torch.empty((hi - lo, do) if last else (N, do), dtype=torch.float32, device=dev)
-            for i in range(0, targets.numel(), chunk):
-                c = targets[i:i + chunk]
-                n = c.numel()
-                nbz = zpos[table.nodes[c, :T].reshape(-1).long()].view(n, T).contiguous()
-                w = table.w[c, :T].contiguous()
+            for i in range(0, n_t, chunk):
+                n = min(chunk, n_t - i)
+                if targets is None:  # rows t_lo + i .. : slices instead of gathers / scatters
+                    r0 = t_lo + i
+                    self_rows = torch.arange(r0, r0 + n, dtype=torch.int32, device=dev)
+                    nb_ids = table.nodes[r0:r0 + n, :T]
+                    w = table.w[r0:r0 + n, :T]
+                    out = h[r0 - lo: r0 - lo + n] if last else h[r0:r0 + n]
+                else:
+                    c = targets[i:i + n]
+                    self_rows = c.to(torch.int32)
+                    nb_ids = table.nodes[c, :T]
+                    w = table.w[c, :T]
+                    out = torch.empty((n, do), dtype=torch.float32, device=dev)
+                if not full_T or targets is not None:
+                    nb_ids, w = nb_ids.contiguous(), w.contiguous()
+                nbz = nb_ids if zpos is None else zpos[nb_ids.reshape(-1).long()].view(n, T)
                 cat = torch.empty((n, din + zw), dtype=torch.float32, device=dev)
                 inv = torch.empty((n,), dtype=torch.float32, device=dev)
-                nat.aggregate_fwd(h_prev, c.to(torch.int32), din, z, nbz, w, zw, cat, inv, tag=f"aggregate_fwd_l{l}")
-                out = torch.empty((n, do), dtype=torch.float32, device=dev)
+                nat.aggregate_fwd(h_prev, self_rows, din, z, nbz, w, zw, cat, inv, tag=f"aggregate_fwd_l{l}")
                 if do <= 128:
                     nat.gemm(cat, w_cat, out, n, do, din + zw, bias=conv.W.bias, act=1, l2norm=True, tag=f"gemm_w_fwd_l{l}")
                 else:
                     nat.gemm(cat, w_cat, out, n, do, din + zw, bias=conv.W.bias, act=1)
                     nat.l2norm_rows(out, torch.empty((n,), dtype=torch.float32, device=dev))
-                if last:
-                    h[c - lo] = out
-                else:
-                    h[c] = out
+                if targets is not None:
+                    if last:
+                        h[c - lo] = out
+                    else:
+                        h[c] = out
             if stats is not None:
-                stats[f"layer{l}"] = {"targets": int(targets.numel()), "z_rows": int(nz)}
+                stats[f"layer{l}"] = {"targets": int(n_t), "z_rows": int(nz)}
             del z, zpos, zrows
             if gather_layer is not None and not last:
                 gather_layer(h, lo, hi)
