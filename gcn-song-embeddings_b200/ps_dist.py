@@ -215,8 +215,9 @@ def embed_shard(trainer, rank: int = None, world_size: int = None, chunk: int = 
     """Node-range sharded full-graph inference (BASELINE.json configs[3]): this rank's rows
     [lo, hi) of the embedding matrix, float32 on the device.  Graph, features and neighbourhood table are replicated.
     exchange=False (the contract): no communication, every rank recomputes the T-hop closure of its range.
-    exchange=True: every rank computes each layer for its own rows only and the layer outputs are all-gathered
-    (L-1 all-gathers of [N, out_dim] fp32 over NCCL / NVLink): same result, 1/world of the work per rank.
+    exchange=True: every rank transforms, projects and aggregates its own rows only; per layer the projected rows
+    (leaky(Q x + b) W2^T, [N, out_dim] fp32) are all-gathered over NCCL / NVLink (Engine._embed_range_exchange): same
+    result, 1 / world of every kernel's work per rank, L all-gathers.
     Returns (lo, hi, embeddings)."""
     rank = trainer.rank if rank is None else rank
     world_size = trainer.world_size if world_size is None else world_size

@@ -350,12 +350,12 @@ class Engine:
         return out, ctx
 
     # ---- inference form of a layer: aggregate AFTER the W projection ------------------------------------------
-    def _projected_rows(self, h_in, din, nz, zrows, conv, l, row_block=1 << 21):
+    def _projected_rows(self, h_in, din, nz, zrows, conv, l, row_block=1 << 21, out=None):
         """zp [nz, do] = leaky(Q x + b) . W[:, din:]^T for the nz needed input rows, in row blocks so that the dh-wide z
         (2 KB per row at dh = 512: 41 GB for 20 M rows) is never materialised as a whole."""
         _, dh, do = self._dims()
         w2 = conv.W.weight.detach()[:, din:]  # [do, dh] view, leading dimension din + dh
-        zp = torch.empty((nz, do), dtype=torch.float32, device="cuda")
+        zp = out if out is not None else torch.empty((nz, do), dtype=torch.float32, device="cuda")
         for b0 in range(0, nz, row_block):
             nb = min(row_block, nz - b0)
             z = torch.empty((nb, dh), dtype=torch.float32, device="cuda")
@@ -630,6 +630,8 @@ class Engine:
             raise IndexError("node range out of bounds")
         if hi == lo:
             return torch.empty((0, do), dtype=torch.float32, device=dev)
+        if gather_layer is not None and do <= 128 and do < dh:
+            return self._embed_range_exchange(feats, lo, hi, chunk, stats, gather_layer, table)
 
         def mark_neighbours(mask, idx):
             for i in range(0, idx.numel(), chunk):
@@ -723,6 +725,53 @@ class Engine:
         out = torch.empty((n_top, do), dtype=torch.float32, device=dev)
         nat.gemm(a1, m.G2.weight, out, n_top, do, do)
         return out
+
+
+def _embed_range_exchange(self, feats, lo, hi, chunk, stats, gather_layer, table):
+    """embed_range with an exchange step, everything sharded: per layer a rank transforms and projects ITS rows only
+    (zp[lo:hi] = leaky(Q x + b) W2^T), the projected table [N, out_dim] is all-gathered (gather_layer), and the rank
+    aggregates its own targets against it.  The next layer needs the layer output for the rank's own rows only, so the
+    projection is the one thing exchanged: L all-gathers of [N, out_dim] fp32, 1 / world of every kernel's work per rank.
+    Row by row the arithmetic is that of the other paths (same kernels, same K order): results are identical."""
+    m = self.model
+    N, T, L = table.n, m.T, m.n_layers
+    in_dims, dh, do = self._dims()
+    dev = feats.device
+    n_own = hi - lo
+    full_T = T == table.Tp
+    h_own = None
+    for l in range(L):
+        conv, din = m.conv_layers[l], in_dims[l]
+        src = feats[lo:hi] if l == 0 else h_own
+        zp = torch.empty((N, do), dtype=torch.float32, device=dev)
+        self._projected_rows(src, din, n_own, None, conv, l, out=zp[lo:hi])
+        gather_layer(zp, lo, hi)
+        w_cat = self._projected_weight(conv, din)
+        h_new = torch.empty((n_own, do), dtype=torch.float32, device=dev)
+        hin = feats if l == 0 else h_own      # layer 0 reads self rows by node id, deeper layers by position in the shard
+        base = lo if l == 0 else 0
+        for i in range(0, n_own, chunk):
+            n = min(chunk, n_own - i)
+            self_rows = torch.arange(base + i, base + i + n, dtype=torch.int32, device=dev)
+            nbz, w = table.nodes[lo + i: lo + i + n, :T], table.w[lo + i: lo + i + n, :T]
+            if not full_T:
+                nbz, w = nbz.contiguous(), w.contiguous()
+            cat = torch.empty((n, din + do), dtype=torch.float32, device=dev)
+            inv = torch.empty((n,), dtype=torch.float32, device=dev)
+            nat.aggregate_fwd(hin, self_rows, din, zp, nbz, w, do, cat, inv, tag=f"aggregate_fwd_l{l}")
+            nat.gemm(cat, w_cat, h_new[i:i + n], n, do, din + do, bias=conv.W.bias, act=1, l2norm=True, tag=f"gemm_w_fwd_l{l}")
+        if stats is not None:
+            stats[f"layer{l}"] = {"targets": int(n_own), "z_rows": int(n_own)}
+        del zp
+        h_own = h_new
+    a1 = torch.empty((n_own, do), dtype=torch.float32, device=dev)
+    nat.gemm(h_own, m.G1.weight, a1, n_own, do, do, bias=m.G1.bias, act=1)
+    out = torch.empty((n_own, do), dtype=torch.float32, device=dev)
+    nat.gemm(a1, m.G2.weight, out, n_own, do, do)
+    return out
+
+
+Engine._embed_range_exchange = _embed_range_exchange
 
 
 class PinSageFunction(torch.autograd.Function):

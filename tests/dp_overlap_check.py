@@ -73,6 +73,16 @@ def main():
     dist.all_reduce(total)
     assert float((total - g_plain).abs().max()) <= 2e-5 * scale  # the exchange sums the ranks' gradients
     assert float((local - g_plain).abs().max()) > 1e-3 * scale   # ... of DIFFERENT batches
+    # node-range sharded inference: the fully sharded exchange path == the no-communication path == a plain embed of the shard
+    t = build(rank, world, False)
+    t.n = 3000
+    lo, hi, e_x = ps_dist.embed_shard(t, exchange=True)
+    _, _, e_c = ps_dist.embed_shard(t, exchange=False)
+    ref = t.model.engine.embed(t._feats(), torch.arange(lo, hi, device="cuda"))
+    assert e_x.shape == (hi - lo, 128)
+    assert torch.equal(e_x, e_c), float((e_x - e_c).abs().max())
+    assert torch.allclose(e_x, ref, rtol=1e-5, atol=1e-6), float((e_x - ref).abs().max())
+    t.close()
     if rank == 0:
         print("dp overlap check ok", flush=True)
     dist.destroy_process_group()
