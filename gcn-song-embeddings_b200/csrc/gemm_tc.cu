@@ -23,6 +23,7 @@
 // 208-210, 259).
 #include "common.cuh"
 #include "../../include/pinsage_b200.h"
+#include <cuda.h>  // CUtensorMap (the encode function is fetched through cudaGetDriverEntryPoint: no link against libcuda)
 #include <mutex>
 
 namespace {
@@ -48,6 +49,8 @@ struct TcArgs {
     const uint8_t* bpack;  // BPACK kernels: hi/lo images of the Q operand, one [2][BN x 128 B] block per (n-tile, k-block)
     uint32_t* mask; int64_t ldm;  // optional sign mask of the activation, one bit per output element (ldm in 32-bit words)
     unsigned long long* dbg;  // development: per-CTA cycle counters of the role waits (ps_gemm_tc_trace), nullptr = off
+    int exp;                  // development (ps_gemm_tc_experiment; results are WRONG when set): bit 0 = the activation producers skip
+                              // their global loads, bit 1 = the weight stream skips its bulk copies, bit 2 = the epilogue skips its stores
     // candidate filter (ps_gemm_filter, packed-weight kernels): no C store; element (i, j) >= filt_thr[j] appends
     // (value, i) to list j: filt_cnt[j]++ -> slot; filt_val / filt_row [j, slot] when slot < filt_cap
     const float* filt_thr; int32_t* filt_cnt; float* filt_val; int32_t* filt_row; int filt_cap;
@@ -115,6 +118,44 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_c, uint64_t adesc, uint6
     asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
                  "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
                  ::"r"(tmem_c), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// TMA tensor-map store of one [32 rows x 32 floats] box (SWIZZLE_128B in shared memory) to C at (col, row); rows / columns
+// beyond the matrix are clipped by the hardware.  Bulk-group completion: wait_read<N> returns once all but the N most recent
+// groups of this thread have finished READING shared memory.
+__device__ __forceinline__ void tma_store_box(const CUtensorMap* map, uint32_t smem_src, int col, int row) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];"
+                 ::"l"(reinterpret_cast<uint64_t>(map)), "r"(col), "r"(row), "r"(smem_src) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait() { asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory"); }
+
+// cta_group::2 forms (tile PAIRS on one 256-row MMA): allocation by one warp of EACH CTA of the pair, MMA and commits by the
+// leader CTA only; a commit arrives on the barrier at this offset in both CTAs
+template <int COLS>
+__device__ __forceinline__ void tmem_alloc2(uint32_t dst_smem) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "n"(COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+template <int COLS>
+__device__ __forceinline__ void tmem_dealloc2(uint32_t taddr) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(COLS) : "memory");
+}
+__device__ __forceinline__ void umma2_tf32(uint32_t tmem_c, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                 "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+                 ::"r"(tmem_c), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma2_commit_multicast(uint32_t bar, uint16_t mask) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"(mask) : "memory");
+}
+// arrive on the mbarrier at the same shared-memory offset in CTA `rank` of the cluster
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t bar, uint32_t rank) {
+    uint32_t raddr;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(raddr) : "r"(bar), "r"(rank));
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(raddr) : "memory");
 }
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
@@ -310,15 +351,21 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 // BPACK: the Q operand (a weight matrix) was split into hi/lo and laid out as K-major SWIZZLE_128B tile images by
 // pack_b_kernel; one thread streams the image of every k-block into the stage with ONE bulk copy, and the eight
 // producer warps only move the activation operand, double-buffered in registers across k-blocks and tiles.
-template <bool PK, bool QK, int BN, bool BPACK, int MASK, int CL>  // MASK: 0 none, 1 = write sign bits (act 1), 2 = apply them (act 2); CL: CTAs per cluster
-__global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(TcArgs a) {
+// CG2 (with CL == 2): the pair runs ONE 256-row tcgen05.mma.cta_group::2 per step instead of two 128-row ones.  Each CTA
+// stages its own 128 rows of A and only HALF of the weight image (BN/2 columns); the tensor cores of the two SMs exchange the
+// halves, so per k-block a CTA writes 64 KB and the MMAs read 96 KB of shared memory instead of 96 KB and 144 KB: the
+// single-CTA 128 x 256 3xTF32 tile is bound by shared-memory bandwidth (240 KB per 1536-cycle k-block against 128 B/clk).
+template <bool PK, bool QK, int BN, bool BPACK, int MASK, int CL, bool CG2 = false>  // MASK: 0 none, 1 = write sign bits (act 1), 2 = apply them (act 2); CL: CTAs per cluster
+__global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(TcArgs a, const __grid_constant__ CUtensorMap cmap) {
     static_assert(!BPACK || (PK && QK), "packed-B kernels take a K-major P and lay Q out K-major");
     static_assert(CL == 1 || (BPACK && CL == 2), "clusters: packed-B kernels, pairs");
-    constexpr int STAGES = BN == 256 ? 2 : 3;
+    static_assert(!CG2 || CL == 2, "cta_group::2 needs the pair");
+    constexpr int STAGES = CG2 ? (BN == 256 ? 2 : 3) : (BN == 256 ? 2 : 3);
     constexpr int HALF = BN / 2;            // columns owned by one epilogue thread
     constexpr int CHUNK_KB = 2;             // k-blocks accumulated in TMEM before the fp32 register drain
     constexpr uint32_t A_BYTES = BM * 128, B_BYTES = BN * 128;
-    constexpr uint32_t STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
+    constexpr uint32_t B_STAGE = CG2 ? B_BYTES / 2 : B_BYTES;  // bytes of ONE of the two (hi / lo) weight tiles a CTA stages
+    constexpr uint32_t STAGE_BYTES = 2 * A_BYTES + 2 * B_STAGE;
     extern __shared__ uint8_t smem_raw[];
     // aligned by pointer arithmetic on the __shared__ array (not through an integer cast), so the compiler keeps the
     // shared address space and emits LDS / STS instead of generic loads / stores
@@ -328,6 +375,9 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(TcArgs a) {
     float* ss_buf = reinterpret_cast<float*>(tmem_slot + 4);  // [2 parities][2 halves][128] partial sums of squares (l2norm)
     float* bias_s = ss_buf + 2 * 2 * 128;                     // [2 parities][BN] bias of the current tile
     float* epi_buf = bias_s + 2 * BN;                         // [8 warps][32 rows][kEpiStride] output staging (coalesced stores)
+    // CG2: the staged C tile leaves through the TMA engine: per accumulate warp two [32 rows x 128 B] boxes (SWIZZLE_128B,
+    // 1024-byte aligned), behind everything else
+    uint8_t* tbox = smem + STAGES * STAGE_BYTES + 8192;
     const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + STAGES);
     const uint32_t tfull0 = smem_u32(bars + 2 * STAGES), tempty0 = smem_u32(bars + 2 * STAGES + 2);
 
@@ -350,11 +400,20 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(TcArgs a) {
     };
 
     if (tid == 0) {
-        for (int s = 0; s < STAGES; ++s) { mbar_init(full0 + 8 * s, kProducerThreads + (BPACK ? 1 : 0)); mbar_init(empty0 + 8 * s, CL); }  // a stage is free when every CTA of the cluster has read it
-        for (int b = 0; b < 2; ++b) { mbar_init(tfull0 + 8 * b, 1); mbar_init(tempty0 + 8 * b, 8); }
+        // full: the producers + the weight stream's expect_tx arrive (+ with CG2, on the leader, the peer's forwarded "my half is staged");
+        // empty: a stage is free when every MMA that reads it has completed: one commit per CTA of the cluster, or the leader's one commit
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(full0 + 8 * s, kProducerThreads + (BPACK ? 1 : 0) + ((CG2 && cta_rank == 0) ? 1 : 0));
+            mbar_init(empty0 + 8 * s, CG2 ? 1 : CL);
+        }
+        // tempty: with CG2 the leader's MMA thread needs BOTH CTAs' accumulate warps to have drained the buffer
+        for (int b = 0; b < 2; ++b) { mbar_init(tfull0 + 8 * b, 1); mbar_init(tempty0 + 8 * b, CG2 ? 16 : 8); }
         fence_barrier_init();
     }
-    if (warp == 16) tmem_alloc<2 * BN>(smem_u32(tmem_slot));
+    if (warp == 16) {
+        if (CG2) tmem_alloc2<2 * BN>(smem_u32(tmem_slot));
+        else tmem_alloc<2 * BN>(smem_u32(tmem_slot));
+    }
     tc_fence_before();
     __syncthreads();
     if (CL > 1) {  // the peer's barriers exist before anything is sent to them
@@ -367,15 +426,20 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(TcArgs a) {
     if (warp >= 16) {
         asm volatile("setmaxnreg.dec.sync.aligned.u32 32;");
         // ------------------------------------------------ MMA issue (one lane of warp 16)
-        if (warp == 16 && lane == 0) {
+        if (warp == 16 && lane == 0 && (!CG2 || cta_rank == 0)) {
             constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((PK ? 0u : 1u) << 15) | ((QK ? 0u : 1u) << 16) |
-                                       (static_cast<uint32_t>(BN >> 3) << 17) | (static_cast<uint32_t>(BM >> 4) << 24);
+                                       (static_cast<uint32_t>(BN >> 3) << 17) | (static_cast<uint32_t>((CG2 ? 2 * BM : BM) >> 4) << 24);
             constexpr uint32_t A_LBO = PK ? 16 : 512, A_SBO = PK ? 1024 : (BM / 32) * 512, A_STEP = PK ? 32 : 2 * (BM / 32) * 512;
             constexpr uint32_t B_LBO = QK ? 16 : 512, B_SBO = QK ? 1024 : (BN / 32) * 512, B_STEP = QK ? 32 : 2 * (BN / 32) * 512;
             constexpr uint32_t A_LAY = PK ? 2u : 1u, B_LAY = QK ? 2u : 1u;
             int stage = 0; uint32_t phase = 0;
             uint32_t gc = 0;  // chunks issued so far (selects the TMEM buffer and its barrier parity)
             long long d_full = 0, d_tempty = 0;
+            if (a.exp & 0x18) {  // development: stagger the CTAs (pairs) in time so that their epilogue stores do not all burst at once
+                const int phase_of = static_cast<int>((blockIdx.x / CL) % 4);
+                const long long t_end = clock64() + static_cast<long long>(phase_of) * ((a.exp & 0x10) ? 16000 : 8000);
+                while (clock64() < t_end) __nanosleep(200);
+            }
             const long long d_t0 = clock64();
             for (int64_t w = w_first; w < total_work; w += w_step) {
                 const Work wk = decode(w);
@@ -389,20 +453,28 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(TcArgs a) {
                         mbar_wait_timed(full0 + 8 * stage, phase, a.dbg, d_full);
                         tc_fence_after();
                         const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
-                        const uint32_t a_hi = sa, a_lo = sa + A_BYTES, b_hi = sa + 2 * A_BYTES, b_lo = b_hi + B_BYTES;
+                        const uint32_t a_hi = sa, a_lo = sa + A_BYTES, b_hi = sa + 2 * A_BYTES, b_lo = b_hi + B_STAGE;
 #pragma unroll
                         for (int s = 0; s < BK / 8; ++s) {
                             const uint64_t dah = make_desc(a_hi + s * A_STEP, A_LBO, A_SBO, A_LAY), dal = make_desc(a_lo + s * A_STEP, A_LBO, A_SBO, A_LAY);
                             const uint64_t dbh = make_desc(b_hi + s * B_STEP, B_LBO, B_SBO, B_LAY), dbl = make_desc(b_lo + s * B_STEP, B_LBO, B_SBO, B_LAY);
-                            umma_tf32(tacc, dal, dbh, idesc, (q | s) != 0);  // a chunk starts a fresh accumulator; small terms first
-                            umma_tf32(tacc, dah, dbl, idesc, 1u);
-                            umma_tf32(tacc, dah, dbh, idesc, 1u);
+                            if (CG2) {
+                                umma2_tf32(tacc, dal, dbh, idesc, (q | s) != 0);
+                                umma2_tf32(tacc, dah, dbl, idesc, 1u);
+                                umma2_tf32(tacc, dah, dbh, idesc, 1u);
+                            } else {
+                                umma_tf32(tacc, dal, dbh, idesc, (q | s) != 0);  // a chunk starts a fresh accumulator; small terms first
+                                umma_tf32(tacc, dah, dbl, idesc, 1u);
+                                umma_tf32(tacc, dah, dbh, idesc, 1u);
+                            }
                         }
-                        if (CL > 1) umma_commit_multicast(empty0 + 8 * stage, static_cast<uint16_t>((1u << CL) - 1));  // ... in every CTA of the cluster
+                        if (CG2) umma2_commit_multicast(empty0 + 8 * stage, 3);  // the stage is free in both CTAs
+                        else if (CL > 1) umma_commit_multicast(empty0 + 8 * stage, static_cast<uint16_t>((1u << CL) - 1));  // ... in every CTA of the cluster
                         else umma_commit(empty0 + 8 * stage);  // frees the smem stage once these MMAs have read it
                         if (++stage == STAGES) { stage = 0; phase ^= 1; }
                     }
-                    umma_commit(tfull0 + 8 * buf);  // publishes the chunk to the accumulate warps
+                    if (CG2) umma2_commit_multicast(tfull0 + 8 * buf, 3);  // publishes the chunk to the accumulate warps of both CTAs
+                    else umma_commit(tfull0 + 8 * buf);  // publishes the chunk to the accumulate warps
                     ++gc;
                 }
             }
@@ -418,8 +490,13 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(TcArgs a) {
                 const uint8_t* src = a.bpack + ((wk.n0 / BN) * nkb + wk.kb_begin) * static_cast<int64_t>(2 * B_BYTES);
                 for (int kb = 0; kb < wk.num_kb; ++kb, src += 2 * B_BYTES) {
                     mbar_wait_timed(empty0 + 8 * stage, phase ^ 1, a.dbg, d_empty);
-                    mbar_arrive_expect_tx(full0 + 8 * stage, 2 * B_BYTES);
-                    if (CL > 1) {  // this CTA's half of the image ([hi | lo]: rank 0 sends hi, rank 1 lo), into both CTAs
+                    if (a.exp & 2) { mbar_arrive(full0 + 8 * stage); if (++stage == STAGES) { stage = 0; phase ^= 1; } continue; }
+                    mbar_arrive_expect_tx(full0 + 8 * stage, 2 * B_STAGE);
+                    if (CG2) {  // this CTA's BN/2 columns of the hi and of the lo tile, into its own stage only
+                        const uint32_t dst = smem_u32(smem + stage * STAGE_BYTES + 2 * A_BYTES);
+                        bulk_g2s(dst, src + cta_rank * B_STAGE, B_STAGE, full0 + 8 * stage);
+                        bulk_g2s(dst + B_STAGE, src + B_BYTES + cta_rank * B_STAGE, B_STAGE, full0 + 8 * stage);
+                    } else if (CL > 1) {  // this CTA's half of the image ([hi | lo]: rank 0 sends hi, rank 1 lo), into both CTAs
                         bulk_g2s_multicast(smem_u32(smem + stage * STAGE_BYTES + 2 * A_BYTES + cta_rank * B_BYTES), src + cta_rank * B_BYTES, B_BYTES,
                                            full0 + 8 * stage, static_cast<uint16_t>((1u << CL) - 1));
                     } else {
@@ -429,6 +506,18 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(TcArgs a) {
                 }
             }
             if (a.dbg) a.dbg[blockIdx.x * 8 + 3] = d_empty;
+        }
+        // ------------------------------------------------ CG2, peer CTA: tell the leader's MMA thread when this CTA's half of a stage is staged
+        if (CG2 && cta_rank != 0 && warp == 18 && lane == 0) {
+            int stage = 0; uint32_t phase = 0;
+            for (int64_t w = w_first; w < total_work; w += w_step) {
+                const Work wk = decode(w);
+                for (int kb = 0; kb < wk.num_kb; ++kb) {
+                    mbar_wait(full0 + 8 * stage, phase);
+                    mbar_arrive_remote(full0 + 8 * stage, 0);
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
         }
     } else if (warp >= 8 && BPACK) {
         asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
@@ -471,7 +560,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(TcArgs a) {
                     have_next = lw < total_work;
                     if (have_next) { lwk = decode(lw); op.init(a.P, a.ldp, a.p_rows, lwk.m0, a.M, t); }
                 }
-                if (have_next) op.template load<0, NJ>(nxt, static_cast<int64_t>(lwk.kb_begin + lkb) * BK, a.K);
+                if (have_next && !(a.exp & 1)) op.template load<0, NJ>(nxt, static_cast<int64_t>(lwk.kb_begin + lkb) * BK, a.K);
                 mbar_wait_timed(empty0 + 8 * stage, phase ^ 1, t == 0 ? a.dbg : nullptr, d_pempty);
                 uint8_t* st = smem + stage * STAGE_BYTES;
 #pragma unroll
@@ -674,7 +763,10 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(TcArgs a) {
                 }
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(tempty0 + 8 * buf);
+                if (lane == 0) {
+                    if (CG2 && cta_rank != 0) mbar_arrive_remote(tempty0 + 8 * buf, 0);  // the MMA thread lives in the leader
+                    else mbar_arrive(tempty0 + 8 * buf);
+                }
             }
             // ---- epilogue on this thread's [row, n0 + half*HALF .. +HALF); the MMA warp is already on the next tile.
             // (Measured with ps_gemm_tc_trace: the accumulate warps spent 60-85 % of the kernel here and the MMA thread
@@ -743,9 +835,37 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(TcArgs a) {
                 for (int j = 0; j < HALF; ++j) acc[j] *= inv_norm;
             }
             const long long d_e1 = (a.dbg && tid == 0) ? clock64() : 0;
+            if (a.exp & 4) continue;
             // Stores go through a per-warp shared-memory transpose, 16 columns at a time: a thread owns one output
             // row, and writing it directly would touch 32 rows x 16 B per instruction (half sectors, 32 LSU
             // wavefronts).  Staged, an instruction writes 8 rows x 64 contiguous bytes (full sectors).
+            if (CG2) {
+                // The tile leaves through the TMA engine.  A thread owns one output row: per round it writes 32 columns of it
+                // into its row of a [32 x 128 B] SWIZZLE_128B box (chunk c at c ^ (row % 8): conflict-free), lane 0 hands the
+                // box to cp.async.bulk.tensor, and the warp goes on with the other box while the engine drains this one.
+                // Two boxes per warp = half of the tile in flight when the warp returns to draining accumulators: the store
+                // traffic (128 KB per tile at the ~30 GB/s one SM gets of the chip's write bandwidth) overlaps the next
+                // tile's MMAs instead of holding the accumulator registers (measured: the register -> STG epilogue was 30 %
+                // of the kernel, profiles/r2q_gemm_ablation.txt).
+                const int row_base = static_cast<int>(wk.m0) + quarter * 32;
+                uint8_t* boxes = tbox + warp * 8192;
+#pragma unroll
+                for (int r = 0; r < HALF / 32; ++r) {
+                    uint8_t* box = boxes + (r & 1) * 4096;
+                    if (lane == 0) bulk_wait_read<1>();  // the store that last read this box (two rounds ago) is done with it
+                    __syncwarp();
+#pragma unroll
+                    for (int c = 0; c < 8; ++c)
+                        *reinterpret_cast<float4*>(box + lane * 128 + ((c ^ (lane & 7)) << 4)) =
+                            make_float4(acc[32 * r + 4 * c], acc[32 * r + 4 * c + 1], acc[32 * r + 4 * c + 2], acc[32 * r + 4 * c + 3]);
+                    fence_proxy_async();
+                    __syncwarp();
+                    if (lane == 0) {
+                        tma_store_box(&cmap, smem_u32(box), static_cast<int>(col0) + 32 * r, row_base);
+                        bulk_commit();
+                    }
+                }
+            } else
             {
                 float* wb = epi_buf + warp * (32 * kEpiStride);
                 const int rr = lane >> 2, cc = (lane & 3) * 4;
@@ -795,6 +915,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(TcArgs a) {
             if (a.dbg && tid == 0) { const long long d_e2 = clock64(); d_epi += d_e2 - d_e0; d_store += d_e2 - d_e1; }
         }
         if (a.dbg && tid == 0) { a.dbg[blockIdx.x * 8 + 5] = d_tfull; a.dbg[blockIdx.x * 8 + 6] = d_epi; a.dbg[blockIdx.x * 8 + 7] = d_store; }
+        if (CG2 && lane == 0) bulk_wait<0>();  // the last boxes have left shared memory (and landed) before the CTA retires
         tc_fence_before();
     }
     __syncthreads();
@@ -802,7 +923,11 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(TcArgs a) {
         asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
         asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
     }
-    if (warp == 16) { tc_fence_after(); tmem_dealloc<2 * BN>(tmem_base); }
+    if (warp == 16) {
+        tc_fence_after();
+        if (CG2) tmem_dealloc2<2 * BN>(tmem_base);
+        else tmem_dealloc<2 * BN>(tmem_base);
+    }
 }
 
 // Split a weight operand into hi/lo and write the K-major SWIZZLE_128B tile images the BPACK kernels stream:
@@ -865,12 +990,42 @@ static int pack_scratch(cudaStream_t stream, size_t bytes, void** out) {
     return PS_OK;
 }
 
-template <bool PK, bool QK, int BN, bool BPACK, int MASK = 0, int CL = 1>
+// 2-D tensor map of the output C [M, N] (row pitch ldc floats) for the TMA store of [32 x 32] fp32 boxes, SWIZZLE_128B
+int make_c_map(CUtensorMap* map, float* C, int64_t M, int64_t N, int64_t ldc) {
+    using Encode = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    static Encode encode = nullptr;
+    if (encode == nullptr) {
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        PS_CUDA_CHECK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q));
+        if (fn == nullptr || q != cudaDriverEntryPointSuccess) return ps_fail(PS_ERR_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
+        encode = reinterpret_cast<Encode>(fn);
+    }
+    const cuuint64_t dims[2] = {static_cast<cuuint64_t>(N), static_cast<cuuint64_t>(M)};
+    const cuuint64_t strides[1] = {static_cast<cuuint64_t>(ldc) * sizeof(float)};
+    const cuuint32_t box[2] = {32, 32};
+    const cuuint32_t estr[2] = {1, 1};
+    const CUresult rc = encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, C, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                               CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (rc != CUDA_SUCCESS) return ps_fail(PS_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d)", static_cast<int>(rc));
+    return PS_OK;
+}
+
+template <bool PK, bool QK, int BN, bool BPACK, int MASK = 0, int CL = 1, bool CG2 = false>
 int launch_tc(TcArgs a, int q_kmajor, cudaStream_t stream) {
     constexpr int STAGES = BN == 256 ? 2 : 3;
-    constexpr size_t smem = STAGES * (2 * BM * 128 + 2 * BN * 128) + (2 * STAGES + 4) * 8 + 16 + (2 * 2 * 128 + 2 * BN + 8 * 32 * kEpiStride) * 4 + 1024;
+    // CG2: half-width weight tiles per stage; behind the barriers / bias the 64 KB of TMA store boxes replace the 20 KB staging buffer
+    constexpr size_t smem = CG2 ? STAGES * (2 * BM * 128 + BN * 128) + 8192 + 8 * 8192 + 1024
+                                : STAGES * (2 * BM * 128 + 2 * BN * 128) + (2 * STAGES + 4) * 8 + 16 + (2 * 2 * 128 + 2 * BN + 8 * 32 * kEpiStride) * 4 + 1024;
     static_assert(smem <= 232448, "shared memory budget");
-    auto kern = gemm_tc_kernel<PK, QK, BN, BPACK, MASK, CL>;
+    auto kern = gemm_tc_kernel<PK, QK, BN, BPACK, MASK, CL, CG2>;
+    alignas(64) CUtensorMap cmap;
+    memset(&cmap, 0, sizeof(cmap));
+    if (CG2 && a.C != nullptr) {
+        const int rc = make_c_map(&cmap, a.C, a.M, a.N, a.ldc);
+        if (rc != PS_OK) return rc;
+    }
     static bool configured = false;
     static int sms = 148;
     if (!configured) {
@@ -910,11 +1065,11 @@ int launch_tc(TcArgs a, int q_kmajor, cudaStream_t stream) {
         attr[0].id = cudaLaunchAttributeClusterDimension;
         attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
         cfg.attrs = attr; cfg.numAttrs = 1;
-        PS_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, a));
+        PS_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, a, cmap));
         return PS_OK;
     }
     const unsigned grid = static_cast<unsigned>(grid64);
-    kern<<<grid, kThreads, smem, stream>>>(a);
+    kern<<<grid, kThreads, smem, stream>>>(a, cmap);
     PS_LAUNCH_CHECK();
     return PS_OK;
 }
@@ -931,13 +1086,15 @@ extern "C" int ps_gemm_tc_prefetch(int on) {
     return old;
 }
 static unsigned long long* g_tc_dbg = nullptr;
+static int g_tc_exp = 0;
+extern "C" int ps_gemm_tc_experiment(int bits) { const int old = g_tc_exp; g_tc_exp = bits; return old; }
 // development: buf = device array of 8 counters per CTA (148 x 8), filled by the next tensor-core GEMM launches:
 // [0] MMA thread total cycles, [1] its wait for operands (full), [2] its wait for a free TMEM buffer, [3] weight-stream wait
 // for a free stage, [4] producer wait for a free stage, [5] accumulate-warp wait for a finished chunk, [6] epilogue cycles
 extern "C" int ps_gemm_tc_trace(unsigned long long* buf) { g_tc_dbg = buf; return PS_OK; }
 static bool g_tc_pack = true;
-static bool g_tc_cluster = true;
-extern "C" int ps_gemm_tc_cluster(int on) { const int old = g_tc_cluster; if (on == 0 || on == 1) g_tc_cluster = on != 0; return old; }
+static int g_tc_cluster = 2;  // 0 = single CTAs, 1 = tile pairs with the weight image multicast, 2 = tile pairs on one cta_group::2 MMA
+extern "C" int ps_gemm_tc_cluster(int mode) { const int old = g_tc_cluster; if (mode >= 0 && mode <= 2) g_tc_cluster = mode; return old; }
 extern "C" int ps_gemm_tc_pack(int on) { const int old = g_tc_pack; if (on == 0 || on == 1) g_tc_pack = on != 0; return old; }
 
 // Returns PS_ERR_UNSUPPORTED (without setting an error) when the shape is outside what this
@@ -967,7 +1124,7 @@ int ps_gemm_tc_launch(const float* P, int64_t ldp, int p_kmajor, const int32_t* 
     if (!accumulate && K > 4 * kMaxChainK) return PS_ERR_UNSUPPORTED;
     if (accumulate && ps_ceil_div(K, splits < 1 ? 1 : splits) > kMaxChainK) splits = static_cast<int>(ps_ceil_div(K, kMaxChainK));
     const int BN = (N > 128) ? 256 : 128;
-    TcArgs a{P, ldp, p_rows, Q, ldq, q_rows, C, ldc, M, N, K, bias, norm_out, act, l2norm, accumulate, 0, 0, 0, 0, nullptr, mask, ldm, g_tc_dbg,
+    TcArgs a{P, ldp, p_rows, Q, ldq, q_rows, C, ldc, M, N, K, bias, norm_out, act, l2norm, accumulate, 0, 0, 0, 0, nullptr, mask, ldm, g_tc_dbg, g_tc_exp,
              nullptr, nullptr, nullptr, nullptr, 0, p_colsum};
     const int64_t num_kb = ps_ceil_div(K, BK);
     if (splits < 1) splits = 1;
@@ -978,20 +1135,23 @@ int ps_gemm_tc_launch(const float* P, int64_t ldp, int p_kmajor, const int32_t* 
     // weight operand (no gather, no split-K) against a tall K-major activation: pre-packed hi/lo images + bulk copies
     const bool packable = p_kmajor && q_rows == nullptr && !accumulate && a.zs == 1;
     // tile PAIRS (2-CTA clusters sharing the weight stream by multicast) once there are enough tiles to fill the SMs with pairs
-    const bool pairs = g_tc_cluster && a.mt * a.nt >= 2 * 148;
+    const bool pairs = g_tc_cluster != 0 && a.mt * a.nt >= 2 * 148;
+    const bool cg2 = pairs && g_tc_cluster == 2 && !(mask == nullptr && act == 2);  // the cta_group::2 kernels store through TMA: no read-modify-write form
+#define PS_TC_PACKED(MASKV)                                                                                                              \
+    do {                                                                                                                                 \
+        if (cg2) return BN == 256 ? launch_tc<true, true, 256, true, MASKV, 2, true>(a, q_kmajor, stream)                                \
+                                  : launch_tc<true, true, 128, true, MASKV, 2, true>(a, q_kmajor, stream);                               \
+        if (pairs) return BN == 256 ? launch_tc<true, true, 256, true, MASKV, 2>(a, q_kmajor, stream)                                    \
+                                    : launch_tc<true, true, 128, true, MASKV, 2>(a, q_kmajor, stream);                                   \
+        return BN == 256 ? launch_tc<true, true, 256, true, MASKV>(a, q_kmajor, stream) : launch_tc<true, true, 128, true, MASKV>(a, q_kmajor, stream); \
+    } while (0)
     if (mask != nullptr) {  // the sign-mask epilogue lives in the packed-weight kernels only
         if (!packable) return PS_ERR_UNSUPPORTED;
-        if (act == 1) {
-            if (pairs) return BN == 256 ? launch_tc<true, true, 256, true, 1, 2>(a, q_kmajor, stream) : launch_tc<true, true, 128, true, 1, 2>(a, q_kmajor, stream);
-            return BN == 256 ? launch_tc<true, true, 256, true, 1>(a, q_kmajor, stream) : launch_tc<true, true, 128, true, 1>(a, q_kmajor, stream);
-        }
-        if (pairs) return BN == 256 ? launch_tc<true, true, 256, true, 2, 2>(a, q_kmajor, stream) : launch_tc<true, true, 128, true, 2, 2>(a, q_kmajor, stream);
-        return BN == 256 ? launch_tc<true, true, 256, true, 2>(a, q_kmajor, stream) : launch_tc<true, true, 128, true, 2>(a, q_kmajor, stream);
+        if (act == 1) PS_TC_PACKED(1);
+        PS_TC_PACKED(2);
     }
-    if (g_tc_pack && packable && M >= 1024) {
-        if (pairs) return BN == 256 ? launch_tc<true, true, 256, true, 0, 2>(a, q_kmajor, stream) : launch_tc<true, true, 128, true, 0, 2>(a, q_kmajor, stream);
-        return BN == 256 ? launch_tc<true, true, 256, true>(a, q_kmajor, stream) : launch_tc<true, true, 128, true>(a, q_kmajor, stream);
-    }
+    if (g_tc_pack && packable && M >= 1024) PS_TC_PACKED(0);
+#undef PS_TC_PACKED
 #define PS_TC_CASE(pk, qk)                                                         \
     if (static_cast<bool>(p_kmajor) == pk && static_cast<bool>(q_kmajor) == qk)     \
         return BN == 256 ? launch_tc<pk, qk, 256, false>(a, q_kmajor, stream) : launch_tc<pk, qk, 128, false>(a, q_kmajor, stream);
@@ -1014,14 +1174,16 @@ extern "C" int ps_gemm_filter(const float* P, int64_t ldp, const float* Q, int64
         (reinterpret_cast<uintptr_t>(P) | reinterpret_cast<uintptr_t>(Q)) % 16 != 0)
         return ps_fail(PS_ERR_UNSUPPORTED, "ps_gemm_filter: shape outside the packed tensor-core path");
     const int BN = (N > 128) ? 256 : 128;
-    TcArgs a{P, ldp, nullptr, Q, ldq, nullptr, nullptr, 0, M, N, K, nullptr, nullptr, 0, 0, 0, 0, 0, 0, 0, nullptr, nullptr, 0, g_tc_dbg,
+    TcArgs a{P, ldp, nullptr, Q, ldq, nullptr, nullptr, 0, M, N, K, nullptr, nullptr, 0, 0, 0, 0, 0, 0, 0, nullptr, nullptr, 0, g_tc_dbg, 0,
              thr, cnt, cand_val, cand_row, cap, nullptr};
     const int64_t num_kb = ps_ceil_div(K, BK);
     a.kb_per_split = static_cast<int>(num_kb);
     a.zs = 1;
     a.mt = ps_ceil_div(M, BM);
     a.nt = ps_ceil_div(N, BN);
-    const bool pairs = g_tc_cluster && a.mt * a.nt >= 2 * 148;
+    const bool pairs = g_tc_cluster != 0 && a.mt * a.nt >= 2 * 148;
+    if (pairs && g_tc_cluster == 2)
+        return BN == 256 ? launch_tc<true, true, 256, true, 0, 2, true>(a, 1, stream) : launch_tc<true, true, 128, true, 0, 2, true>(a, 1, stream);
     if (pairs) return BN == 256 ? launch_tc<true, true, 256, true, 0, 2>(a, 1, stream) : launch_tc<true, true, 128, true, 0, 2>(a, 1, stream);
     return BN == 256 ? launch_tc<true, true, 256, true>(a, 1, stream) : launch_tc<true, true, 128, true>(a, 1, stream);
 }

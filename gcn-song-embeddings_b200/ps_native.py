@@ -43,6 +43,7 @@ _SIGNATURES = {
     "ps_gemm_tc_prefetch": ([c_int], c_int),
     "ps_gemm_tc_cluster": ([c_int], c_int),
     "ps_gemm_tc_trace": ([c_void_p], c_int),
+    "ps_gemm_tc_experiment": ([c_int], c_int),
     "ps_graph_create": ([c_void_p, c_void_p, c_int64, c_int64, c_int64, ctypes.POINTER(c_void_p), c_void_p], c_int),
     "ps_graph_destroy": ([c_void_p], c_int),
     "ps_graph_use_indptr32": ([c_void_p, c_int], c_int),

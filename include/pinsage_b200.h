@@ -120,14 +120,19 @@ int ps_gemm_tc_reserve_sms(int n);
 /* 1 (default) = the tensor-core producers prefetch their next operand rows into L2 (a tile / 6 k-blocks ahead), 0 = off
  * (A/B measurements).  Returns the previous setting. */
 int ps_gemm_tc_prefetch(int on);
-/* 1 (default) = tall packed-weight GEMMs run as 2-CTA clusters on tile pairs that share the weight stream by TMA
- * multicast, 0 = one CTA per tile (A/B measurements).  Returns the previous setting. */
-int ps_gemm_tc_cluster(int on);
+/* How tall packed-weight GEMMs use thread-block clusters: 0 = one CTA per tile; 1 = 2-CTA clusters on tile pairs that share
+ * the weight stream by TMA multicast (cta_group::1 MMAs); 2 = tile pairs on ONE 256-row tcgen05.mma.cta_group::2 per step,
+ * each CTA staging half of the weight image.  Returns the previous mode. */
+int ps_gemm_tc_cluster(int mode);
 /* Development: device array of 8 uint64 counters per CTA that the following tensor-core GEMM launches fill with the
  * cycles their warp roles spent waiting (NULL = off): [0] MMA-issue total, [1] its wait for operands, [2] its wait for a
  * free accumulator, [3] weight-stream wait for a free stage, [4] producer wait for a free stage, [5] accumulate-warp
  * wait for a finished chunk, [6] epilogue. */
 int ps_gemm_tc_trace(unsigned long long* buf);
+/* Development: ablation switches for the tensor-core kernels (results are WRONG while set): bit 0 = the activation producers skip
+ * their global loads, bit 1 = the weight stream skips its bulk copies, bit 2 = the epilogue skips its stores.  Returns the
+ * previous value; 0 restores normal operation. */
+int ps_gemm_tc_experiment(int bits);
 
 /* ---- K4+K6: neighbour gather + importance-weighted mean fused with the concat
  *      (pinsage_model.py:195-197,202,208):

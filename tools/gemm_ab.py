@@ -30,9 +30,21 @@ calls = {
 }
 import sys
 dbg = torch.zeros(148 * 8, dtype=torch.int64, device="cuda")
-for cl in (1,):
+ref = {}
+for cl in (1, 2):
     nat.lib().ps_gemm_tc_cluster(cl)
-    print("cluster", cl, {k: round(timed(f), 4) for k, f in calls.items()})
+    # correctness of the mode first: same shape, against mode 1 (same MMAs in the same order: bit-equal expected) and fp64
+    zc = torch.empty(nz, dh, device="cuda"); mc = torch.empty(nz, dh // 32, dtype=torch.int32, device="cuda")
+    nat.gemm(feats, Qw, zc, nz, dh, din, p_rows=zrows, bias=Qb, act=1, mask=mc); torch.cuda.synchronize()
+    want = torch.nn.functional.leaky_relu(feats[zrows.long()][:4096].double() @ Qw.double().t() + Qb.double(), 0.01)
+    err = float((zc[:4096].double() - want).abs().max() / want.abs().max())
+    tail = torch.nn.functional.leaky_relu(feats[zrows.long()][-300:].double() @ Qw.double().t() + Qb.double(), 0.01)
+    err_t = float((zc[-300:].double() - tail).abs().max() / tail.abs().max())
+    if cl == 1:
+        ref["z"], ref["m"] = zc.clone(), mc.clone()
+    print("cluster mode", cl, "q_fwd max err vs fp64 (first 4096 rows / last 300 rows):", err, err_t,
+          "| == mode 1:", bool(torch.equal(zc, ref["z"])) and bool(torch.equal(mc, ref["m"])), flush=True)
+    print("cluster", cl, {k: round(timed(f), 4) for k, f in calls.items()}, flush=True)
     for k, f in calls.items():
         if "wgrad" in k:
             continue
@@ -40,3 +52,10 @@ for cl in (1,):
         d = dbg.view(148, 8).double().mean(0).tolist()
         print("   ", k, "MMA-thread total %.0f kcyc | waits: operands %.0f%%, free TMEM %.0f%% | B-stream wait-empty %.0f%% | producer wait-empty %.0f%% | acc-warp wait-tfull %.0f%%, epilogue %.0f%% (of which the staged stores %.0f%%)"
               % (d[0] / 1e3, 100 * d[1] / d[0], 100 * d[2] / d[0], 100 * d[3] / d[0], 100 * d[4] / d[0], 100 * d[5] / d[0], 100 * d[6] / d[0], 100 * d[7] / d[0]))
+lib = nat.lib()
+for cl in (1, 2):
+    lib.ps_gemm_tc_cluster(cl)
+    for bits, what in ((0, "normal"), (1, "no A loads"), (2, "no B copies"), (4, "no stores"), (7, "MMA + drain only")):
+        lib.ps_gemm_tc_experiment(bits)
+        print("cluster", cl, "%-18s" % what, {k[:10]: round(timed(f), 4) for k, f in calls.items() if "wgrad" not in k}, flush=True)
+    lib.ps_gemm_tc_experiment(0)
