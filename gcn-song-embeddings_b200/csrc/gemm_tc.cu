@@ -358,9 +358,10 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 template <bool PK, bool QK, int BN, bool BPACK, int MASK, int CL, bool CG2 = false>  // MASK: 0 none, 1 = write sign bits (act 1), 2 = apply them (act 2); CL: CTAs per cluster
 __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(TcArgs a, const __grid_constant__ CUtensorMap cmap) {
     static_assert(!BPACK || (PK && QK), "packed-B kernels take a K-major P and lay Q out K-major");
-    static_assert(CL == 1 || (BPACK && CL == 2), "clusters: packed-B kernels, pairs");
+    static_assert(CL == 1 || (BPACK && CL == 2) || (CG2 && CL == 2 && !PK && !QK), "clusters: pairs; packed-B kernels, or the cta_group::2 weight-gradient kernel");
     static_assert(!CG2 || CL == 2, "cta_group::2 needs the pair");
-    constexpr int STAGES = CG2 ? (BN == 256 ? 2 : 3) : (BN == 256 ? 2 : 3);
+    constexpr int BNS = CG2 ? BN / 2 : BN;  // columns of the Q operand ONE CTA stages
+    constexpr int STAGES = (CG2 && !BPACK) ? 3 : (BN == 256 ? 2 : 3);  // the cta_group::2 weight-gradient kernel: 64 KB stages, no store boxes
     constexpr int HALF = BN / 2;            // columns owned by one epilogue thread
     constexpr int CHUNK_KB = 2;             // k-blocks accumulated in TMEM before the fp32 register drain
     constexpr uint32_t A_BYTES = BM * 128, B_BYTES = BN * 128;
@@ -390,11 +391,20 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(TcArgs a, const __
     if (CL > 1) asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(cta_rank));
     const int64_t w_first = CL > 1 ? blockIdx.x / CL : blockIdx.x;
     const int64_t w_step = CL > 1 ? gridDim.x / CL : gridDim.x;
-    const int64_t total_work = CL > 1 ? ((a.mt + CL - 1) / CL) * a.nt : a.mt * a.nt * a.zs;
+    const int64_t m_pairs = (a.mt + CL - 1) / CL;
+    const int64_t total_work = CL > 1 ? m_pairs * a.nt * (BPACK ? 1 : a.zs) : a.mt * a.nt * a.zs;
     auto decode = [&](int64_t w) -> Work {
-        if (CL > 1) {  // n-tile fastest, then tile pairs; no split-K on this path; a pair's second tile may lie beyond M
+        if (CL > 1 && BPACK) {  // n-tile fastest, then tile pairs; no split-K on this path; a pair's second tile may lie beyond M
             const int64_t n_idx = w % a.nt, mp = w / a.nt;
             return {(mp * CL + cta_rank) * BM, n_idx * static_cast<int64_t>(BN), 0, static_cast<int>((a.K + BK - 1) / BK)};
+        }
+        if (CL > 1) {  // weight gradients: tile pairs x n-tiles x k-splits
+            const int64_t n_idx = w % a.nt, rest = w / a.nt;
+            const int64_t mp = rest % m_pairs, z = rest / m_pairs;
+            const int64_t nkb = (a.K + BK - 1) / BK;
+            const int64_t b = z * a.kb_per_split;
+            const int64_t e = min(nkb, b + a.kb_per_split);
+            return {(mp * CL + cta_rank) * BM, n_idx * static_cast<int64_t>(BN), static_cast<int>(b), static_cast<int>(e - b)};
         }
         return decode_work(a, w, BN);
     };
@@ -430,7 +440,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(TcArgs a, const __
             constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((PK ? 0u : 1u) << 15) | ((QK ? 0u : 1u) << 16) |
                                        (static_cast<uint32_t>(BN >> 3) << 17) | (static_cast<uint32_t>((CG2 ? 2 * BM : BM) >> 4) << 24);
             constexpr uint32_t A_LBO = PK ? 16 : 512, A_SBO = PK ? 1024 : (BM / 32) * 512, A_STEP = PK ? 32 : 2 * (BM / 32) * 512;
-            constexpr uint32_t B_LBO = QK ? 16 : 512, B_SBO = QK ? 1024 : (BN / 32) * 512, B_STEP = QK ? 32 : 2 * (BN / 32) * 512;
+            constexpr uint32_t B_LBO = QK ? 16 : 512, B_SBO = QK ? 1024 : (BNS / 32) * 512, B_STEP = QK ? 32 : 2 * (BNS / 32) * 512;
             constexpr uint32_t A_LAY = PK ? 2u : 1u, B_LAY = QK ? 2u : 1u;
             int stage = 0; uint32_t phase = 0;
             uint32_t gc = 0;  // chunks issued so far (selects the TMEM buffer and its barrier parity)
@@ -583,7 +593,8 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(TcArgs a, const __
         // exposed ~4 memory latencies per k-block (index -> row, twice); this keeps the whole next k-block in flight.
         const int t = tid - 8 * 32;
         using OpA = Operand<false, BM, true>;
-        using OpB = Operand<false, BN, false>;
+        using OpB = Operand<false, BNS, false>;  // CG2: this CTA's half of the Q columns
+        const int64_t n_half = CG2 ? static_cast<int64_t>(cta_rank) * BNS : 0;
         LoadCursor<OpA, OpB> lc;
         lc.w = w_first; lc.kb = 0;
         lc.valid = lc.w < total_work;
@@ -593,7 +604,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(TcArgs a, const __
             lc.k0 = static_cast<int64_t>(wk.kb_begin) * BK;
             lc.m0 = wk.m0; lc.n0 = wk.n0;
             lc.a.init(a.P, a.ldp, a.p_rows, wk.m0, a.M, t);
-            lc.b.init(a.Q, a.ldq, a.q_rows, wk.n0, a.N, t);
+            lc.b.init(a.Q, a.ldq, a.q_rows, wk.n0 + n_half, a.N, t);
         }
         const uint32_t offa = lc.a.off0, offb = lc.b.off0;  // shared-memory offsets depend on the thread only
         const uint32_t smem0 = smem_u32(smem);
@@ -625,7 +636,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(TcArgs a, const __
                     lc.k0 = static_cast<int64_t>(wk.kb_begin) * BK;
                     lc.m0 = wk.m0; lc.n0 = wk.n0;
                     lc.a.init(a.P, a.ldp, a.p_rows, wk.m0, a.M, t);
-                    lc.b.init(a.Q, a.ldq, a.q_rows, wk.n0, a.N, t);
+                    lc.b.init(a.Q, a.ldq, a.q_rows, wk.n0 + n_half, a.N, t);
                 }
             } else {
                 lc.k0 += BK;
@@ -660,7 +671,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(TcArgs a, const __
                     float4 l;
                     l.x = v.x - __uint_as_float(__float_as_uint(v.x) & kHiMask); l.y = v.y - __uint_as_float(__float_as_uint(v.y) & kHiMask);
                     l.z = v.z - __uint_as_float(__float_as_uint(v.z) & kHiMask); l.w = v.w - __uint_as_float(__float_as_uint(v.w) & kHiMask);
-                    *reinterpret_cast<float4*>(st + 2 * A_BYTES + B_BYTES + offb + j * OpB::kStep) = l;
+                    *reinterpret_cast<float4*>(st + 2 * A_BYTES + B_STAGE + offb + j * OpB::kStep) = l;
                 }
                 fence_proxy_async();
                 mbar_arrive(full0 + 8 * stage);
@@ -672,7 +683,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(TcArgs a, const __
                         if (kp < a.K && lc.kb + kPrefetchKb < lc.nkb) {
                             const int line = t & 7;  // a Q row of BN floats = BN / 32 lines, a P row of BM floats = BM / 32 lines
                             const int64_t qrow = lc.b.rows ? static_cast<int64_t>(__ldg(lc.b.rows + kp)) : kp;
-                            if (line < BN / 32 && lc.n0 + line * 32 < a.N) asm volatile("prefetch.global.L2 [%0];" ::"l"(a.Q + qrow * a.ldq + lc.n0 + line * 32));
+                            if (line < BNS / 32 && lc.n0 + n_half + line * 32 < a.N) asm volatile("prefetch.global.L2 [%0];" ::"l"(a.Q + qrow * a.ldq + lc.n0 + n_half + line * 32));
                             if (line < BM / 32 && lc.m0 + line * 32 < a.M) asm volatile("prefetch.global.L2 [%0];" ::"l"(a.P + kp * a.ldp + lc.m0 + line * 32));
                         }
                     }
@@ -839,7 +850,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(TcArgs a, const __
             // Stores go through a per-warp shared-memory transpose, 16 columns at a time: a thread owns one output
             // row, and writing it directly would touch 32 rows x 16 B per instruction (half sectors, 32 LSU
             // wavefronts).  Staged, an instruction writes 8 rows x 64 contiguous bytes (full sectors).
-            if (CG2) {
+            if (CG2 && BPACK) {
                 // The tile leaves through the TMA engine.  A thread owns one output row: per round it writes 32 columns of it
                 // into its row of a [32 x 128 B] SWIZZLE_128B box (chunk c at c ^ (row % 8): conflict-free), lane 0 hands the
                 // box to cp.async.bulk.tensor, and the warp goes on with the other box while the engine drains this one.
@@ -915,7 +926,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(TcArgs a, const __
             if (a.dbg && tid == 0) { const long long d_e2 = clock64(); d_epi += d_e2 - d_e0; d_store += d_e2 - d_e1; }
         }
         if (a.dbg && tid == 0) { a.dbg[blockIdx.x * 8 + 5] = d_tfull; a.dbg[blockIdx.x * 8 + 6] = d_epi; a.dbg[blockIdx.x * 8 + 7] = d_store; }
-        if (CG2 && lane == 0) bulk_wait<0>();  // the last boxes have left shared memory (and landed) before the CTA retires
+        if (CG2 && BPACK && lane == 0) bulk_wait<0>();  // the last boxes have left shared memory (and landed) before the CTA retires
         tc_fence_before();
     }
     __syncthreads();
@@ -1014,10 +1025,12 @@ int make_c_map(CUtensorMap* map, float* C, int64_t M, int64_t N, int64_t ldc) {
 
 template <bool PK, bool QK, int BN, bool BPACK, int MASK = 0, int CL = 1, bool CG2 = false>
 int launch_tc(TcArgs a, int q_kmajor, cudaStream_t stream) {
-    constexpr int STAGES = BN == 256 ? 2 : 3;
-    // CG2: half-width weight tiles per stage; behind the barriers / bias the 64 KB of TMA store boxes replace the 20 KB staging buffer
-    constexpr size_t smem = CG2 ? STAGES * (2 * BM * 128 + BN * 128) + 8192 + 8 * 8192 + 1024
-                                : STAGES * (2 * BM * 128 + 2 * BN * 128) + (2 * STAGES + 4) * 8 + 16 + (2 * 2 * 128 + 2 * BN + 8 * 32 * kEpiStride) * 4 + 1024;
+    constexpr int STAGES = (CG2 && !BPACK) ? 3 : (BN == 256 ? 2 : 3);
+    // CG2: half-width Q tiles per stage.  Packed-weight kernels: behind the barriers / bias the 64 KB of TMA store boxes replace the
+    // 20 KB staging buffer; weight-gradient kernel: three stages and the staging buffer (its partials leave as atomics)
+    constexpr size_t kMisc = (2 * STAGES + 4) * 8 + 16 + (2 * 2 * 128 + 2 * BN + 8 * 32 * kEpiStride) * 4 + 1024;
+    constexpr size_t smem = CG2 ? (BPACK ? STAGES * (2 * BM * 128 + BN * 128) + 8192 + 8 * 8192 + 1024 : STAGES * (2 * BM * 128 + BN * 128) + kMisc)
+                                : STAGES * (2 * BM * 128 + 2 * BN * 128) + kMisc;
     static_assert(smem <= 232448, "shared memory budget");
     auto kern = gemm_tc_kernel<PK, QK, BN, BPACK, MASK, CL, CG2>;
     alignas(64) CUtensorMap cmap;
@@ -1053,7 +1066,7 @@ int launch_tc(TcArgs a, int q_kmajor, cudaStream_t stream) {
     int64_t grid64 = total < usable ? total : usable;
     if (g_tc_waves > 1 && total >= static_cast<int64_t>(sms) * 8 * g_tc_waves) grid64 = static_cast<int64_t>(sms) * g_tc_waves;
     if (CL > 1) {  // one cluster per tile pair: an even grid, at most one CTA per SM
-        const int64_t pairs = ps_ceil_div(a.mt, CL) * a.nt;
+        const int64_t pairs = ps_ceil_div(a.mt, CL) * a.nt * (BPACK ? 1 : a.zs);
         int64_t clusters = usable / CL;
         if (clusters > pairs) clusters = pairs;
         cudaLaunchConfig_t cfg = {};
@@ -1093,8 +1106,8 @@ extern "C" int ps_gemm_tc_experiment(int bits) { const int old = g_tc_exp; g_tc_
 // for a free stage, [4] producer wait for a free stage, [5] accumulate-warp wait for a finished chunk, [6] epilogue cycles
 extern "C" int ps_gemm_tc_trace(unsigned long long* buf) { g_tc_dbg = buf; return PS_OK; }
 static bool g_tc_pack = true;
-static int g_tc_cluster = 2;  // 0 = single CTAs, 1 = tile pairs with the weight image multicast, 2 = tile pairs on one cta_group::2 MMA
-extern "C" int ps_gemm_tc_cluster(int mode) { const int old = g_tc_cluster; if (mode >= 0 && mode <= 2) g_tc_cluster = mode; return old; }
+static int g_tc_cluster = 3;  // 0 = single CTAs, 1 = tile pairs with the weight image multicast, 2 = tile pairs on one cta_group::2 MMA, 3 = 2 + the weight-gradient GEMMs on pairs as well
+extern "C" int ps_gemm_tc_cluster(int mode) { const int old = g_tc_cluster; if (mode >= 0 && mode <= 3) g_tc_cluster = mode; return old; }
 extern "C" int ps_gemm_tc_pack(int on) { const int old = g_tc_pack; if (on == 0 || on == 1) g_tc_pack = on != 0; return old; }
 
 // Returns PS_ERR_UNSUPPORTED (without setting an error) when the shape is outside what this
@@ -1136,7 +1149,7 @@ int ps_gemm_tc_launch(const float* P, int64_t ldp, int p_kmajor, const int32_t* 
     const bool packable = p_kmajor && q_rows == nullptr && !accumulate && a.zs == 1;
     // tile PAIRS (2-CTA clusters sharing the weight stream by multicast) once there are enough tiles to fill the SMs with pairs
     const bool pairs = g_tc_cluster != 0 && a.mt * a.nt >= 2 * 148;
-    const bool cg2 = pairs && g_tc_cluster == 2 && !(mask == nullptr && act == 2);  // the cta_group::2 kernels store through TMA: no read-modify-write form
+    const bool cg2 = pairs && g_tc_cluster >= 2 && !(mask == nullptr && act == 2);  // the cta_group::2 kernels store through TMA: no read-modify-write form
 #define PS_TC_PACKED(MASKV)                                                                                                              \
     do {                                                                                                                                 \
         if (cg2) return BN == 256 ? launch_tc<true, true, 256, true, MASKV, 2, true>(a, q_kmajor, stream)                                \
@@ -1152,6 +1165,8 @@ int ps_gemm_tc_launch(const float* P, int64_t ldp, int p_kmajor, const int32_t* 
     }
     if (g_tc_pack && packable && M >= 1024) PS_TC_PACKED(0);
 #undef PS_TC_PACKED
+    if (g_tc_cluster == 3 && !p_kmajor && !q_kmajor && accumulate && BN == 256 && a.mt >= 2 && a.mt * a.nt * a.zs >= 148)
+        return launch_tc<false, false, 256, false, 0, 2, true>(a, q_kmajor, stream);  // weight gradients on tile pairs (cta_group::2)
 #define PS_TC_CASE(pk, qk)                                                         \
     if (static_cast<bool>(p_kmajor) == pk && static_cast<bool>(q_kmajor) == qk)     \
         return BN == 256 ? launch_tc<pk, qk, 256, false>(a, q_kmajor, stream) : launch_tc<pk, qk, 128, false>(a, q_kmajor, stream);
@@ -1182,7 +1197,7 @@ extern "C" int ps_gemm_filter(const float* P, int64_t ldp, const float* Q, int64
     a.mt = ps_ceil_div(M, BM);
     a.nt = ps_ceil_div(N, BN);
     const bool pairs = g_tc_cluster != 0 && a.mt * a.nt >= 2 * 148;
-    if (pairs && g_tc_cluster == 2)
+    if (pairs && g_tc_cluster >= 2)
         return BN == 256 ? launch_tc<true, true, 256, true, 0, 2, true>(a, 1, stream) : launch_tc<true, true, 128, true, 0, 2, true>(a, 1, stream);
     if (pairs) return BN == 256 ? launch_tc<true, true, 256, true, 0, 2>(a, 1, stream) : launch_tc<true, true, 128, true, 0, 2>(a, 1, stream);
     return BN == 256 ? launch_tc<true, true, 256, true>(a, 1, stream) : launch_tc<true, true, 128, true>(a, 1, stream);

@@ -122,7 +122,8 @@ int ps_gemm_tc_reserve_sms(int n);
 int ps_gemm_tc_prefetch(int on);
 /* How tall packed-weight GEMMs use thread-block clusters: 0 = one CTA per tile; 1 = 2-CTA clusters on tile pairs that share
  * the weight stream by TMA multicast (cta_group::1 MMAs); 2 = tile pairs on ONE 256-row tcgen05.mma.cta_group::2 per step,
- * each CTA staging half of the weight image.  Returns the previous mode. */
+ * each CTA staging half of the weight image and the output tile leaving through TMA tensor-map stores (default); 3 = 2, and the
+ * weight-gradient GEMMs (activation x activation, split-K) run on pairs as well.  Returns the previous mode. */
 int ps_gemm_tc_cluster(int mode);
 /* Development: device array of 8 uint64 counters per CTA that the following tensor-core GEMM launches fill with the
  * cycles their warp roles spent waiting (NULL = off): [0] MMA-issue total, [1] its wait for operands, [2] its wait for a

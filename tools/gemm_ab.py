@@ -31,7 +31,7 @@ calls = {
 import sys
 dbg = torch.zeros(148 * 8, dtype=torch.int64, device="cuda")
 ref = {}
-for cl in (1, 2):
+for cl in (1, 2, 3):
     nat.lib().ps_gemm_tc_cluster(cl)
     # correctness of the mode first: same shape, against mode 1 (same MMAs in the same order: bit-equal expected) and fp64
     zc = torch.empty(nz, dh, device="cuda"); mc = torch.empty(nz, dh // 32, dtype=torch.int32, device="cuda")
@@ -44,6 +44,17 @@ for cl in (1, 2):
         ref["z"], ref["m"] = zc.clone(), mc.clone()
     print("cluster mode", cl, "q_fwd max err vs fp64 (first 4096 rows / last 300 rows):", err, err_t,
           "| == mode 1:", bool(torch.equal(zc, ref["z"])) and bool(torch.equal(mc, ref["m"])), flush=True)
+    gq = torch.zeros(dh, din, device="cuda"); gbb = torch.zeros(dh, device="cuda")
+    nat.gemm_wgrad(zc, feats, gq, dh, din, nz, x_rows=zrows, splits=74, bias_grad=gbb); torch.cuda.synchronize()
+    if cl == 1:
+        ref["gq"], ref["gb"] = gq.clone(), gbb.clone()
+        sub = slice(0, 200_000)
+        want_g = zc[sub].double().t() @ feats[zrows[sub].long()].double()
+        g_sub = torch.zeros(dh, din, device="cuda")
+        nat.gemm_wgrad(zc[sub], feats, g_sub, dh, din, 200_000, x_rows=zrows[sub].contiguous(), splits=74)
+        print("   wgrad (200k rows) max err vs fp64, scaled:", float((g_sub.double() - want_g).abs().max() / want_g.abs().max()))
+    print("   wgrad vs mode 1: max |diff| / max |g| =", float((gq - ref["gq"]).abs().max() / ref["gq"].abs().max()),
+          " bias grad:", float((gbb - ref["gb"]).abs().max() / ref["gb"].abs().max()), flush=True)
     print("cluster", cl, {k: round(timed(f), 4) for k, f in calls.items()}, flush=True)
     for k, f in calls.items():
         if "wgrad" in k:
@@ -53,7 +64,7 @@ for cl in (1, 2):
         print("   ", k, "MMA-thread total %.0f kcyc | waits: operands %.0f%%, free TMEM %.0f%% | B-stream wait-empty %.0f%% | producer wait-empty %.0f%% | acc-warp wait-tfull %.0f%%, epilogue %.0f%% (of which the staged stores %.0f%%)"
               % (d[0] / 1e3, 100 * d[1] / d[0], 100 * d[2] / d[0], 100 * d[3] / d[0], 100 * d[4] / d[0], 100 * d[5] / d[0], 100 * d[6] / d[0], 100 * d[7] / d[0]))
 lib = nat.lib()
-for cl in (1, 2):
+for cl in ((1, 2) if '--ablate' in sys.argv else ()):
     lib.ps_gemm_tc_cluster(cl)
     for bits, what in ((0, "normal"), (1, "no A loads"), (2, "no B copies"), (4, "no stores"), (7, "MMA + drain only")):
         lib.ps_gemm_tc_experiment(bits)
