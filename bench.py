@@ -199,6 +199,13 @@ def roofline_from_profile(summary, steps, peaks):
     else:
         achieved = top["bytes"] / top["launches"] / (per_launch_ms * 1e-3) / 1e9
         peak, unit, bound = peaks["hbm_gbs"], "GB/s", "hbm"
+        traffic = measured_traffic(tag)
+        extra = {"note": "algorithmic bytes count EVERY gathered neighbour row (targets x T rows of the transformed table per launch, "
+                         "SURVEY.md section 8d); rows referenced by several targets are partly served by L2, so `frac` can exceed 1 "
+                         "while the DRAM pins move `traffic` bytes: `frac_dram_measured` is that traffic over the same time"}
+        if traffic:
+            extra["dram_gbs"] = round(traffic / (per_launch_ms * 1e-3) / 1e9, 1)
+            extra["frac_dram_measured"] = round(traffic / (per_launch_ms * 1e-3) / 1e9 / peak, 4)
     shares = {k: round(v["ms"] / total, 4) for k, v in sorted(summary.items(), key=lambda kv: -kv[1]["ms"])[:8]}
     return {"kernel": tag, "bound": bound, "achieved": round(achieved, 2), "peak": peak, "unit": unit,
             "frac": round(achieved / peak, 4), "traffic": measured_traffic(tag), "peak_source": peaks["source"],
