@@ -237,6 +237,8 @@ extern "C" int ps_train_step(const ps_step_args* a, ps_stream_t stream_) {
             Timed t(stream, "gemm_w_wgrad", l, 2.0 * dout * (din + dh) * lp.n, gemm_bytes(dout, din + dh, lp.n));
             PS_TRY(ps_gemm_wgrad(lb.d_pre, dout, lb.cat, din + dh, nullptr, pr.gWw, din + dh, dout, din + dh, lp.n, splits_for(dout, din + dh, lp.n), pr.gWb, stream));
         }
+        if (l == 0 && L >= 2 && a->upper_grads_event != nullptr)  // every gradient but layer 0's Q.weight / Q.bias is final from here on
+            PS_CUDA_CHECK(cudaEventRecord(static_cast<cudaEvent_t>(a->upper_grads_event), stream));
         {
             const double pairs = static_cast<double>(lp.n) * T;
             Timed t(stream, "aggregate_bwd", l, 2.0 * pairs * dout, pairs * (dout * 4 + 12) + static_cast<double>(lp.nz) * (dout * 4 + 8));
@@ -264,8 +266,6 @@ extern "C" int ps_train_step(const ps_step_args* a, ps_stream_t stream_) {
             PS_TRY(ps_scatter_add_rows(lb.d_self, din, lp.self_rows, lb.d_h_in, din, lp.n, din, stream));
             d_h = lb.d_h_in;
         }
-        if (l == 1 && a->upper_grads_event != nullptr)  // everything but layer 0's gradients is final from here on
-            PS_CUDA_CHECK(cudaEventRecord(static_cast<cudaEvent_t>(a->upper_grads_event), stream));
     }
     if (a->emb_out != nullptr) *a->emb_out = b.out;
     return PS_OK;

@@ -73,11 +73,11 @@ def allreduce_mean_(flat: torch.Tensor, world_size: int):
 
 
 class GradSync:
-    """The per-step gradient exchange of one replica.  The flat gradient is summed over the ranks in two parts: the
-    layers above layer 0 and the head are final about half way through the backward (ps_train_step records an event
-    there), so their allreduce runs on NCCL's stream while layer 0's backward -- the bulk of the step -- still computes;
-    only layer 0's own gradients (conv_layers.0.*, the first parameters of the flat buffer) are exchanged after the
-    last kernel.  The mean's 1 / world_size is folded into the Adam kernel (FlatAdam.grad_scale)."""
+    """The per-step gradient exchange of one replica.  The flat gradient is summed over the ranks in two parts: everything
+    but layer 0's Q.weight / Q.bias is final once layer 0's W gradient is done (ps_train_step records an event there),
+    so that part is reduced on NCCL's stream while the aggregation backward and the two largest GEMMs of the step still
+    compute; only conv_layers.0.Q.* (the first parameters of the flat buffer, 0.5 MB) are exchanged after the last
+    kernel.  The mean's 1 / world_size is folded into the Adam kernel (FlatAdam.grad_scale)."""
 
     def __init__(self, trainer, world_size):
         self.engine, self.world = trainer.model.engine, world_size

@@ -578,7 +578,7 @@ class Engine:
             a.batch, a.diag_out = prep.batch.data_ptr(), out.data_ptr() + 4
         emb_ptr = nat.c_void_p()
         a.emb_out = nat.ctypes.pointer(emb_ptr)
-        # data parallel (ps_dist.GradSync): an event the step records once only layer 0's gradients are still being computed
+        # data parallel (ps_dist.GradSync): an event the step records once only layer 0's Q gradients are still being computed
         self.upper_grads_event, self.upper_grads_offset = None, 0
         if getattr(self, "want_upper_grads_event", False) and L >= 2:
             ev = getattr(self, "_upper_ev", None)
@@ -587,7 +587,8 @@ class Engine:
                 ev.record()  # creates the underlying cudaEvent_t
             a.upper_grads_event = ev.cuda_event
             self.upper_grads_event = ev
-            self.upper_grads_offset = sum(p.numel() for p in m.conv_layers[0].parameters())
+            q0 = m.conv_layers[0].Q  # flat order = named_parameters(): conv_layers.0.Q.weight, Q.bias come first
+            self.upper_grads_offset = q0.weight.numel() + q0.bias.numel()
         nat.train_step(a, launches=10 + 13 * L)
         n_top = prep.plan.layers[-1].n
         off = emb_ptr.value - ws.data_ptr()

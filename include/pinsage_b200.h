@@ -291,9 +291,9 @@ typedef struct ps_step_args {
     float* loss_out;                     /* [1] */
     const int64_t* batch; float* diag_out; /* optional diagnostics: batch int64 [B,3] node ids, diag_out [2] (ps_train_diagnostics) */
     float** emb_out;                     /* optional HOST location that receives the device pointer of the [n_top, out_dim] embeddings */
-    void* upper_grads_event;             /* optional cudaEvent_t recorded on `stream` once the gradients of every layer above layer 0 and of
-                                            the head are final (before layer 0's backward, about half of the step): a data-parallel caller
-                                            starts the allreduce of that part of flat_grad behind it while layer 0's backward runs */
+    void* upper_grads_event;             /* optional cudaEvent_t recorded on `stream` once every gradient except layer 0's Q.weight / Q.bias is
+                                            final (after layer 0's W weight gradient: the aggregation backward and the two largest GEMMs of the
+                                            step still follow): a data-parallel caller starts the allreduce of that part of flat_grad behind it */
 } ps_step_args;
 int64_t ps_train_step_workspace(const ps_step_args* args);
 int ps_train_step(const ps_step_args* args, ps_stream_t stream);
