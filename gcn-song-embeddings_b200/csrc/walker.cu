@@ -68,17 +68,6 @@ __device__ __forceinline__ Philox philox4x32_10(uint32_t c0, uint32_t c1, uint32
     return {c0, c1, c2, c3};
 }
 
-// one CSR hop: uniform successor of `node` picked by x
-template <typename PtrT>
-__device__ __forceinline__ uint32_t hop(const PtrT* __restrict__ indptr, const int32_t* __restrict__ indices,
-                                        uint32_t node, uint32_t x) {
-    const PtrT beg = __ldg(indptr + node);
-    const PtrT end = __ldg(indptr + node + 1);
-    const uint32_t deg = static_cast<uint32_t>(end - beg);
-    if (deg == 0) return node;  // unreachable after ps_graph_create's degree check
-    return static_cast<uint32_t>(__ldg(indices + beg + __umulhi(x, deg)));
-}
-
 // warp-cooperative bitonic sort (descending) of a[0..P) in shared memory, P a power of two >= 32 (T > 256)
 template <typename K>
 __device__ __forceinline__ void warp_bitonic_sort_desc(K* a, int P, int lane) {
