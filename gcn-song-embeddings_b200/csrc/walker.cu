@@ -3,22 +3,23 @@
 // do_random_walks (reference pinsage_model.py:32-53) and the dense [n, N+C] float64
 // histogram + torch.topk of sample_neighborhood[_topt] (:88-107).
 //
-// Design (B200): one warp per source node, 32 steps per pass, one step per lane.
-//  * Walk.  The chain of a source is a sequence of i.i.d. segments that all start at the
-//    source; the restart flag of step j depends only on Philox(seed, source, j).  A ballot
-//    of the 32 flags gives every lane its position inside its segment; round k advances
-//    the lanes at position k from their left neighbour's item (one shuffle), so a pass
-//    costs max-segment-length rounds (about 3 at alpha = 0.85) and every lane computes
-//    exactly one Philox block.  A segment that crosses the pass boundary is carried in a
-//    register.  The source's own adjacency row bounds are loaded once.
-//  * Histogram.  Visited ids go into a per-warp open-addressed hash table in shared
-//    memory (id -> 16-bit count); the dense row of the reference is never materialised
-//    and the trace never goes to HBM (unless the caller asks for it).
-//  * Top-T.  The table is compacted in place; a warp-wide MSB-first radix select over the
-//    48-bit key (count, ~id) finds the T-th largest entry in <= 6 passes; only the
-//    selected <= T entries are sorted (bitonic, 64-bit keys) -> canonical order
-//    (count desc, id asc); weight = count / n_hops in IEEE double.
-// HBM traffic per step is the two CSR hops (indptr pair + one neighbour id each).
+// Design (B200): one warp per source node; draws keyed by Philox4x32-10(counter = (step, source, 0, 0), key = seed), so
+// the result does not depend on the launch shape and a CPU restatement reproduces it bit for bit.
+//  * Walk (walk_source).  The chain of a source is a sequence of i.i.d. segments that all start at the source; whether
+//    step j ends its segment depends only on Philox(j, source).  Steps that START a segment (85 % at alpha = 0.85) are
+//    walked in place, 32 * U at a time, from the source's row bounds held in registers; a step whose successor continues
+//    the segment appends (j + 1, item) to a list in shared memory, and list rounds advance the pending continuations 32
+//    at a time.  Every lane computes one Philox block per step it walks.
+//  * Top-T, two kernels with identical results:
+//      walk_sort_kernel (n_hops <= 512, T <= 256): the trace stays in shared memory (4 B per step), is sorted in registers
+//        (lane-major bitonic network), run lengths of the sorted trace are the visit counts, the boundary count class
+//        comes from packed tallies and the "R smallest ids of that class" from prefix ballots;
+//      walk_topt_kernel (everything else): per-warp open-addressed hash table (id -> 16-bit count), in-place
+//        compaction, class tallies, MSB-first radix passes over the significant id bits of the boundary class.
+//    Both end with the <= T selected keys sorted (count desc, id asc) and weight = count / n_hops in IEEE double; the
+//    dense row of the reference is never materialised and the trace never goes to HBM (unless the caller asks for it).
+// HBM traffic per step is the two CSR hops (row bounds + one neighbour id each): in practice one random 64-byte DRAM
+// burst per step, which is what bounds the kernel.
 #include "common.cuh"
 #include "../../include/pinsage_b200.h"
 
