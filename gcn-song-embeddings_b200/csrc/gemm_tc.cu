@@ -19,6 +19,10 @@
 //              bias + leaky_relu + row L2-normalise and store, or red.global.add for split-K
 //              weight gradients.  Registers are rebalanced with setmaxnreg (168 / 56 / 32 of the 96 per thread the CTA is launched with: the
 //              pool only holds what the CTA's own warps give back).
+// Large GEMMs run on PAIRS of CTAs (2-CTA clusters, two vertically adjacent tiles): one 256-row
+// tcgen05.mma.cta_group::2 per step issued by the leader, each CTA staging its own A rows and half of the Q operand; the
+// packed-weight kernels hand their output tiles to the TMA engine (cp.async.bulk.tensor stores of SWIZZLE_128B boxes).
+// ps_gemm_tc_cluster selects the mode.
 // Replaces nn.Linear / AddmmBackward of ConvLayer and the head (pinsage_model.py:201,
 // 208-210, 259).
 #include "common.cuh"
