@@ -1031,15 +1031,19 @@ int launch_tc(TcArgs a, int q_kmajor, cudaStream_t stream) {
         const int rc = make_c_map(&cmap, a.C, a.M, a.N, a.ldc);
         if (rc != PS_OK) return rc;
     }
-    static bool configured = false;
-    static int sms = 148;
-    if (!configured) {
+    // per DEVICE: a process may drive several devices through ps_set_device (function attributes and the SM count belong to one)
+    constexpr int kMaxDevices = 64;
+    static bool configured[kMaxDevices] = {};
+    static int sm_count[kMaxDevices] = {};
+    int dev = 0;
+    PS_CUDA_CHECK(cudaGetDevice(&dev));
+    const int slot = dev >= 0 && dev < kMaxDevices ? dev : 0;
+    if (!configured[slot] || slot != dev) {
         PS_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-        int dev = 0;
-        PS_CUDA_CHECK(cudaGetDevice(&dev));
-        PS_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-        configured = true;
+        PS_CUDA_CHECK(cudaDeviceGetAttribute(&sm_count[slot], cudaDevAttrMultiProcessorCount, dev));
+        configured[slot] = true;
     }
+    const int sms = sm_count[slot];
     void* pack = nullptr;
     if (BPACK) {
         const int64_t nkb = ps_ceil_div(a.K, BK);
