@@ -406,15 +406,16 @@ def test_flat_adam_equals_torch_adam():
 
 @pytest.mark.parametrize("M,N,K", [(40_001 // 4 * 4, 512, 256), (38_000, 128, 768), (37_900, 512, 128), (75_000, 256, 64)])
 def test_gemm_tile_pairs_with_multicast_weights(nat, M, N, K):
-    """Tall packed-weight GEMMs run as 2-CTA clusters on tile PAIRS that share the weight stream by TMA multicast
-    (odd tile counts leave a phantom second tile): forward with row gather + bias + leaky + sign mask, the act=2 backward
-    with that mask, the l2norm epilogue -- against fp64 products, and bit-equal to the one-CTA-per-tile kernel."""
+    """Tall packed-weight GEMMs run as 2-CTA clusters on tile PAIRS (odd tile counts leave a phantom second tile), either
+    sharing the weight stream by TMA multicast (cluster mode 1) or on one tcgen05.mma.cta_group::2 with TMA tensor-map stores
+    (modes 2 / 3, the default): forward with row gather + bias + leaky + sign mask, the act=2 backward with that mask, the
+    l2norm epilogue -- against fp64 products, and bit-equal across all modes incl. the one-CTA-per-tile kernel."""
     torch.manual_seed(M + N)
     table = torch.randn(M + 5000, K, device="cuda")
     rows = torch.randint(0, M + 5000, (M,), device="cuda", dtype=torch.int32)
     W = torch.randn(N, K, device="cuda") * 0.1; b = torch.randn(N, device="cuda")
     outs = {}
-    for cl in (1, 0):
+    for cl in (1, 0, 2, 3):
         old = nat.lib().ps_gemm_tc_cluster(cl)
         y = torch.empty(M, N, device="cuda"); mask = torch.zeros(M, N // 32, dtype=torch.int32, device="cuda")
         nat.gemm(table, W, y, M, N, K, p_rows=rows, bias=b, act=1, mask=mask)
@@ -435,5 +436,30 @@ def test_gemm_tile_pairs_with_multicast_weights(nat, M, N, K):
     assert rel(d, (S.double() @ V.double()) * torch.where(y > 0, 1.0, 0.01).double()) < 1e-5
     if out is not None:
         assert rel(out, want / want.norm(dim=1, keepdim=True)) < 1e-5
-    for a_, b_ in zip(outs[1], outs[0]):
-        assert (a_ is None and b_ is None) or torch.equal(a_, b_)   # same arithmetic per output element
+    for other in (0, 2, 3):
+        for a_, b_ in zip(outs[1], outs[other]):
+            assert (a_ is None and b_ is None) or torch.equal(a_, b_)   # same arithmetic per output element
+
+
+@pytest.mark.parametrize("M,N,K,gather", [(512, 256, 300_000, True), (384, 256, 150_001 // 4 * 4, False), (1024, 512, 90_000, True)])
+def test_gemm_wgrad_on_tile_pairs(nat, M, N, K, gather):
+    """Weight-gradient GEMMs (activation x activation, split-K, bias gradient from the operand tiles) on tile pairs with
+    cta_group::2 (cluster mode 3, the default) against fp64 and against the one-CTA kernels (mode 1): same products, the
+    split-K partials meet in atomics, so equal to rounding."""
+    torch.manual_seed(K)
+    dY = torch.randn(K, M, device="cuda") * 0.1
+    X = torch.randn(K + 1000, N, device="cuda")
+    rows = torch.randint(0, K + 1000, (K,), device="cuda", dtype=torch.int32) if gather else None
+    Xg = X[rows.long()] if gather else X[:K]
+    want = dY.double().t() @ Xg.double()
+    want_b = dY.double().sum(0)
+    got = {}
+    for cl in (1, 3):
+        old = nat.lib().ps_gemm_tc_cluster(cl)
+        g = torch.zeros(M, N, device="cuda"); gb = torch.zeros(M, device="cuda")
+        nat.gemm_wgrad(dY, X, g, M, N, K, x_rows=rows, splits=-(-148 * 4 // (-(-M // 128) * -(-N // 128))), bias_grad=gb)
+        nat.lib().ps_gemm_tc_cluster(old)
+        assert rel(g, want) < 2e-6 and rel(gb, want_b) < 2e-6, (cl, rel(g, want), rel(gb, want_b))
+        got[cl] = (g, gb)
+    scale = float(want.abs().max())
+    assert float((got[1][0] - got[3][0]).abs().max()) < 1e-5 * scale
