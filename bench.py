@@ -175,8 +175,9 @@ def walk_roofline(n_sources, n_hops, ms, peaks):
     return out
 
 
-def roofline_from_profile(summary, steps, peaks):
-    """Pick the kernel with the largest share of the step and report it against its bound."""
+def roofline_from_profile(summary, steps, peaks, dims=None):
+    """Pick the kernel with the largest share of the step and report it against its bound.  dims = (din, dh, dout, T) of
+    the workload: lets the aggregation kernels be reported in SURVEY.md section 8d's algorithmic unit."""
     if not summary:
         return None
     total = sum(v["ms"] for v in summary.values())
@@ -200,9 +201,23 @@ def roofline_from_profile(summary, steps, peaks):
         achieved = top["bytes"] / top["launches"] / (per_launch_ms * 1e-3) / 1e9
         peak, unit, bound = peaks["hbm_gbs"], "GB/s", "hbm"
         traffic = measured_traffic(tag)
-        extra = {"note": "algorithmic bytes count EVERY gathered neighbour row (targets x T rows of the transformed table per launch, "
-                         "SURVEY.md section 8d); rows referenced by several targets are partly served by L2, so `frac` can exceed 1 "
-                         "while the DRAM pins move `traffic` bytes: `frac_dram_measured` is that traffic over the same time"}
+        extra = {}
+        if tag.startswith("aggregate_fwd") and dims is not None:
+            # SURVEY.md section 8d's unit per target: (T+1) gathered INPUT rows of Din floats + T (index, weight) pairs + the Do-wide
+            # output row.  The kernel itself gathers the TRANSFORMED rows (Dh wide, Q applied once per distinct row instead of once
+            # per gathered row), so the bytes it addresses per target are larger: both figures are reported.
+            din, dh, dout, T = dims
+            din_l = din if tag.endswith("_l0") else dout
+            per_target_kernel = T * dh * 4 + din_l * 4 + T * 8 + 4 + (din_l + dh) * 4 + 4
+            per_target_survey = (T + 1) * din_l * 4 + T * 8 + dout * 4
+            targets = top["bytes"] / top["launches"] / per_target_kernel
+            extra = {"kernel_addressed_gbs": round(achieved, 1), "kernel_addressed_bytes_per_target": per_target_kernel,
+                     "algorithmic_bytes_per_target": per_target_survey, "targets_per_launch": round(targets)}
+            top = dict(top, bytes=targets * per_target_survey * top["launches"])
+            achieved = top["bytes"] / top["launches"] / (per_launch_ms * 1e-3) / 1e9
+        extra["note"] = ("`achieved` = SURVEY.md section 8d's algorithmic bytes per target x targets per launch over the launch time; the kernel "
+                         "addresses more (Dh-wide transformed rows, `kernel_addressed_gbs`), part of which L2 serves: `traffic` / "
+                         "`frac_dram_measured` are the bytes the DRAM pins really move (ncu) over the same time")
         if traffic:
             extra["dram_gbs"] = round(traffic / (per_launch_ms * 1e-3) / 1e9, 1)
             extra["frac_dram_measured"] = round(traffic / (per_launch_ms * 1e-3) / 1e9 / peak, 4)
@@ -707,7 +722,7 @@ def run_ours(args, wl):
         line["prep_timing_ms"] = {k: round(v * 1e3 / t["n"], 3) for k, v in t.items() if k != "n"}
     line["extra"] = extra
     if rank == 0:
-        line["roofline"] = roofline_from_profile(prof, args.steps, peaks)
+        line["roofline"] = roofline_from_profile(prof, args.steps, peaks, dims=(din, 512, 128, T))
         line["peaks"] = peaks
         if world == 1 and not args.no_cpu_baseline:
             os.sched_setaffinity(0, allowed_cpus)
