@@ -257,3 +257,37 @@ def test_batch_construction_equals_reference_draws(golden):
     fixed, _ = pst.sample_hard_negatives(all_ids, pos_batch, nbhds, 10, 100, reference_compat=False)
     assert all(int(fixed[i, 2]) in g["nb_nodes"][int(fixed[i, 0]), 10:100] for i in range(B))
     assert float(pst.batch_variance(torch.from_numpy(g["var_h"]))) == pytest.approx(float(g["var"]), rel=1e-6)
+
+
+def test_bench_roofline_helpers():
+    """bench.py's roofline arithmetic (no GPU): the aggregation kernel is reported in SURVEY 8d's algorithmic unit with the
+    kernel-addressed and DRAM-measured figures beside it; a GEMM against the tensor peak; the walker against HBM and the
+    measured random-access ceiling."""
+    import importlib.util
+    import sys
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(ROOT, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    argv, sys.argv = sys.argv, ["bench.py"]
+    try:
+        spec.loader.exec_module(bench)
+    finally:
+        sys.argv = argv
+    peaks = {"hbm_gbs": 6548.5, "tflops": 1381.6, "source": "measured"}
+    n, T, din, dh, do = 98_499, 50, 256, 512, 128
+    per_target_kernel = T * dh * 4 + din * 4 + T * 8 + 4 + (din + dh) * 4 + 4
+    summary = {"aggregate_fwd_l0": {"ms": 1.166 * 30, "launches": 30, "flops": 0.0, "bytes": 30.0 * n * per_target_kernel},
+               "gemm_q_wgrad_l0": {"ms": 1.07 * 30, "launches": 30, "flops": 30 * 1.72e11, "bytes": 0.0}}
+    r = bench.roofline_from_profile(summary, 30, peaks, dims=(din, dh, do, T))
+    assert r["kernel"] == "aggregate_fwd_l0" and r["bound"] == "hbm" and r["unit"] == "GB/s"
+    assert r["algorithmic_bytes_per_target"] == (T + 1) * din * 4 + T * 8 + do * 4 == 53_136
+    assert abs(r["achieved"] - n * 53_136 / 1.166e-3 / 1e9) < 1.0 and abs(r["frac"] - r["achieved"] / 6548.5) < 1e-3
+    assert r["kernel_addressed_gbs"] > r["achieved"] and r["targets_per_launch"] == n
+    if r["traffic"]:
+        assert abs(r["frac_dram_measured"] - r["traffic"] / 1.166e-3 / 1e9 / 6548.5) < 1e-3
+    summary["gemm_q_wgrad_l0"]["ms"] = 2.0 * 30
+    g = bench.roofline_from_profile(summary, 30, peaks, dims=(din, dh, do, T))
+    assert g["kernel"] == "gemm_q_wgrad_l0" and g["bound"] == "tensor" and abs(g["achieved"] - 1.72e11 / 2.0e-3 / 1e12) < 0.01
+    w = bench.walk_roofline(1_000_000, 500, 9.87, peaks)
+    assert abs(w["frac_of_hbm"] - 5e8 * 28 / 9.87e-3 / 1e9 / 6548.5) < 1e-3
+    if "random_access_bound" in w:
+        assert 0.5 < w["random_access_bound"]["frac_of_bound"] <= 1.05 and w["frac_of_hbm_dram_measured"] > w["frac_of_hbm"]
