@@ -48,6 +48,23 @@ def _worker(rank, world, port, out):
     gathered = [torch.zeros_like(model.weight) for _ in range(world)]
     dist.all_gather(gathered, model.weight.data)
     assert torch.equal(gathered[0], gathered[1])
+    # GradSync (the object attach() installs) without a recorded event: one plain sum over the whole flat buffer, the mean's
+    # 1 / world folded into the optimiser (grad_scale) when it offers that, else divided here
+    class _Obj:
+        pass
+    for has_scale in (True, False):
+        tr, eng, optim = _Obj(), _Obj(), _Obj()
+        eng.flat_grad = torch.full((64,), float(rank + 1))
+        tr.model = _Obj(); tr.model.engine = eng; tr.optimizer = optim
+        if has_scale:
+            optim.grad_scale = 1.0
+        sync = ps_dist.GradSync(tr, world)
+        assert eng.want_upper_grads_event is True
+        sync()
+        if has_scale:
+            assert optim.grad_scale == 1.0 / world and torch.equal(eng.flat_grad, torch.full((64,), 3.0))
+        else:
+            assert torch.equal(eng.flat_grad, torch.full((64,), 1.5))
     # max-over-ranks timing and node-range shards
     assert ps_dist.max_over_ranks(float(rank)) == float(world - 1)
     lo, hi = ps_dist.shard_range(1001, rank, world)
